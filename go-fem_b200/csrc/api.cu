@@ -1,0 +1,406 @@
+// api.cu -- the extern "C" surface declared in include/femb200.h.
+#include "common.cuh"
+#include <cstring>
+#include <vector>
+
+using namespace femb200;
+
+extern "C" {
+
+int femb200_abi_version(void) { return FEMB200_ABI_VERSION; }
+
+int femb200_ctx_create(int device, femb200_ctx **out) {
+  if (!out) return FEMB200_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FEMB200_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FEMB200_ERR_CUDA;
+  if (prop.major != 10) return FEMB200_ERR_CUDA; // sm_100a cubin only: no other architecture can run it
+  femb200_ctx *ctx = new femb200_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+#define CK(e)                                                          \
+  do {                                                                 \
+    if ((e) != cudaSuccess) { delete ctx; return FEMB200_ERR_CUDA; }   \
+  } while (0)
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaDeviceGetDefaultMemPool(&ctx->pool, device));
+  uint64_t thr = UINT64_MAX; // keep freed blocks in the pool: repeated assemblies never hit cudaMalloc
+  CK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  CK(cudaMalloc((void **)&ctx->d_err, sizeof(unsigned long long)));
+  CK(cudaMalloc((void **)&ctx->d_scalars, 8 * sizeof(int64_t)));
+  CK(cudaMallocHost((void **)&ctx->h_scalars, 8 * sizeof(int64_t)));
+  CK(cudaMallocHost((void **)&ctx->h_err, sizeof(unsigned long long)));
+  for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
+#undef CK
+  *out = ctx;
+  return 0;
+}
+
+void femb200_ctx_destroy(femb200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->cub_tmp) cudaFreeAsync(ctx->cub_tmp, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_err);
+  cudaFree(ctx->d_scalars);
+  cudaFreeHost(ctx->h_scalars);
+  cudaFreeHost(ctx->h_err);
+  for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int femb200_ctx_set_stream(femb200_ctx *ctx, void *s) {
+  if (!ctx) return FEMB200_ERR_BAD_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return 0;
+}
+
+const char *femb200_last_cuda_error(const femb200_ctx *ctx) { return ctx ? ctx->last_cuda_error.c_str() : "no context"; }
+int64_t femb200_kernel_launches(const femb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int femb200_sync(femb200_ctx *ctx) {
+  if (!ctx) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int femb200_assembler_create(femb200_ctx *ctx, const double *nodes, int64_t n_nodes, int32_t mdpn,
+                             int32_t on_device, femb200_assembler **out) {
+  if (!ctx || !out || n_nodes < 0 || mdpn < 1 || mdpn > 16 || (n_nodes > 0 && !nodes)) return FEMB200_ERR_BAD_ARG;
+  *out = nullptr;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  femb200_assembler *ga = new femb200_assembler();
+  ga->ctx = ctx;
+  ga->n_nodes = n_nodes;
+  ga->mdpn = mdpn;
+  if (on_device) {
+    ga->d_nodes = nodes;
+    ga->own_nodes = false;
+  } else {
+    double *d = nullptr;
+    int rc = dev_alloc(ctx, &d, (size_t)n_nodes * 3);
+    if (rc) { delete ga; return rc; }
+    if (n_nodes) {
+      cudaError_t e = cudaMemcpyAsync(d, nodes, sizeof(double) * 3 * n_nodes, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // caller memory may be released after return
+      if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); delete ga; return FEMB200_ERR_CUDA; }
+    }
+    ga->d_nodes = d;
+  }
+  ga->K.n_rows = n_nodes * mdpn; // assembler.go:22
+  int rc = dev_alloc(ctx, &ga->K.indptr, (size_t)ga->K.n_rows + 1);
+  if (rc) { delete ga; return rc; }
+  cudaMemsetAsync(ga->K.indptr, 0, sizeof(int64_t) * (ga->K.n_rows + 1), ctx->stream);
+  *out = ga;
+  return 0;
+}
+
+static void free_plan(femb200_assembler *ga) {
+  femb200_ctx *ctx = ga->ctx;
+  dev_free(ctx, ga->plan.n2e_ptr);
+  dev_free(ctx, ga->plan.n2e_t);
+  dev_free(ctx, ga->plan.pos16);
+  dev_free(ctx, ga->plan.blkptr);
+  ga->plan = LastPlan();
+}
+
+void femb200_assembler_destroy(femb200_assembler *ga) {
+  if (!ga) return;
+  femb200_ctx *ctx = ga->ctx;
+  cudaSetDevice(ctx->device);
+  free_plan(ga);
+  dev_free(ctx, ga->K.indptr); dev_free(ctx, ga->K.indices); dev_free(ctx, ga->K.values);
+  if (ga->own_nodes) { double *d = const_cast<double *>(ga->d_nodes); dev_free(ctx, d); }
+  cudaStreamSynchronize(ctx->stream);
+  delete ga;
+}
+
+// descriptor -> ElemShape + packed table blob [C | w | N | dN]
+static int prepare(const femb200_assembler *ga, const femb200_elem_desc *d, ElemShape *sh, std::vector<double> *blob) {
+  if (!d || !d->Npg || !d->dNpg || !d->wpg || !d->C || !d->dofmap) return FEMB200_ERR_BAD_ARG;
+  if (d->d < 1 || d->d > kMaxD || d->nn < 1 || d->nn > kMaxNN || d->ndn < 1 || d->ndn > kMaxNdn || d->nqp < 1 ||
+      d->dimC < 1 || d->dimC > kMaxDimC || d->model_dofs_per_node != ga->mdpn)
+    return FEMB200_ERR_BAD_ARG;
+  sh->d = d->d; sh->nn = d->nn; sh->ndn = d->ndn; sh->nqp = d->nqp; sh->dimC = d->dimC; sh->bkind = d->bkind;
+  sh->mdpn = ga->mdpn;
+  // distinct dofmap values, ascending (U), and dof -> index in U
+  bool seen[16] = {};
+  for (int i = 0; i < d->ndn; ++i) {
+    if (d->dofmap[i] < 0 || d->dofmap[i] >= ga->mdpn) return FEMB200_ERR_BAD_ARG;
+    seen[d->dofmap[i]] = true;
+  }
+  sh->nu = 0;
+  for (int i = 0; i < kMaxNdn; ++i) { sh->umap[i] = 0; sh->dof2u[i] = 0; }
+  for (int m = 0; m < ga->mdpn && m < 16; ++m)
+    if (seen[m]) {
+      if (sh->nu >= kMaxNdn) return FEMB200_ERR_BAD_ARG;
+      sh->umap[sh->nu++] = m;
+    }
+  sh->identity = (sh->nu == d->ndn) && (d->ndn == ga->mdpn);
+  for (int i = 0; i < d->ndn; ++i) {
+    for (int k = 0; k < sh->nu; ++k) if (sh->umap[k] == d->dofmap[i]) sh->dof2u[i] = k;
+    if (d->dofmap[i] != i) sh->identity = false;
+  }
+  TabLayout tl = tab_layout(d->d, d->nn, d->nqp, d->dimC);
+  blob->assign(tl.total, 0.0);
+  std::memcpy(blob->data() + tl.offC, d->C, sizeof(double) * d->dimC * d->dimC);
+  std::memcpy(blob->data() + tl.offW, d->wpg, sizeof(double) * d->nqp);
+  std::memcpy(blob->data() + tl.offN, d->Npg, sizeof(double) * d->nqp * d->nn);
+  std::memcpy(blob->data() + tl.offDN, d->dNpg, sizeof(double) * d->nqp * d->d * d->nn);
+  return numeric_supported(*sh) ? 0 : FEMB200_ERR_UNSUPPORTED;
+}
+
+static int decode_error(femb200_assembler *ga) {
+  unsigned long long w = *ga->ctx->h_err;
+  if (w == kNoError) return 0;
+  ga->err_kind = (int)(w & 0xf);
+  ga->err_qp = (int)((w >> 4) & 0xfff);
+  ga->err_elem = (int64_t)(w >> 16);
+  if (ga->err_kind == FEMB200_ERR_NODE_OOB) ga->err_qp = -1;
+  return ga->err_kind;
+}
+
+// uploads (if needed), narrows to int32 and validates the connectivity
+static int stage_conn(femb200_assembler *ga, const void *conn, bool is64, bool on_device, int64_t n, int nn,
+                      int32_t **conn32, void **staged) {
+  femb200_ctx *ctx = ga->ctx;
+  *staged = nullptr;
+  int rc;
+  if ((rc = dev_alloc(ctx, conn32, (size_t)n))) return rc;
+  const void *d_in = conn;
+  if (!on_device && n) {
+    size_t bytes = (size_t)n * (is64 ? 8 : 4);
+    FEMB_CUDA_OK(ctx, cudaMallocAsync(staged, bytes, ctx->pool, ctx->stream));
+    FEMB_CUDA_OK(ctx, cudaMemcpyAsync(*staged, conn, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_in = *staged;
+  }
+  return narrow_and_validate_conn(ga, d_in, is64, n, nn, *conn32);
+}
+
+int femb200_add_isoparametric(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn,
+                              int32_t conn_is_int64, int32_t conn_on_device, int64_t n_elem) {
+  if (!ga || n_elem < 0 || (n_elem > 0 && !conn)) return FEMB200_ERR_BAD_ARG;
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  ga->err_kind = 0; ga->err_elem = -1; ga->err_qp = -1;
+  ElemShape sh;
+  std::vector<double> blob;
+  int rc = prepare(ga, desc, &sh, &blob);
+  if (rc) { ga->err_kind = rc; return rc; }
+  for (float &f : ga->phase_ms) f = 0.f;
+  const int64_t launches0 = ctx->launches;
+
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
+  *ctx->h_err = kNoError;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+  int32_t *conn32 = nullptr;
+  void *staged = nullptr;
+  double *d_tab = nullptr;
+  SymbolicResult sym;
+  auto cleanup = [&]() {
+    dev_free(ctx, conn32);
+    if (staged) cudaFreeAsync(staged, st);
+    dev_free(ctx, d_tab);
+    dev_free(ctx, sym.blkcols);
+  };
+  auto drop_sym = [&]() {
+    dev_free(ctx, sym.n2e_ptr); dev_free(ctx, sym.n2e_t); dev_free(ctx, sym.pos16); dev_free(ctx, sym.blkptr);
+    dev_free(ctx, sym.csr.indptr); dev_free(ctx, sym.csr.indices); dev_free(ctx, sym.csr.values);
+  };
+  rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged);
+  if (!rc) rc = dev_alloc(ctx, &d_tab, blob.size());
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
+  }
+  if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; return rc; }
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], st));
+
+  rc = symbolic_phase(ga, sh, conn32, n_elem, &sym); // synchronises once (nblk, max row length, error word)
+  if (rc == -1) rc = decode_error(ga);
+  if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; }
+
+  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), conn32, n_elem, &sym);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st); // blob / caller buffers are released after this point
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
+  }
+  if (!rc) rc = decode_error(ga);
+  if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; } // K untouched (:118-120)
+
+  // commit: K += this call (assembler_isoparametric.go:121); keep the plan for the slot-map query
+  free_plan(ga);
+  ga->plan.nn = sh.nn; ga->plan.nu = sh.nu; ga->plan.n_elem = n_elem;
+  ga->plan.n2e_ptr = sym.n2e_ptr; ga->plan.n2e_t = sym.n2e_t; ga->plan.pos16 = sym.pos16; ga->plan.blkptr = sym.blkptr;
+  rc = csr_merge_into(ga, &sym.csr);
+  cleanup();
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[6], st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (rc) { ga->err_kind = rc; return rc; }
+  float ms = 0;
+  const int pairs[6][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {4, 5}, {5, 6}};
+  for (int i = 0; i < 6; ++i)
+    if (cudaEventElapsedTime(&ms, ctx->ev[pairs[i][0]], ctx->ev[pairs[i][1]]) == cudaSuccess) ga->phase_ms[i] = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]) == cudaSuccess) ga->phase_ms[6] = ms;
+  ga->phase_ms[7] = (float)(ctx->launches - launches0);
+  return 0;
+}
+
+int femb200_last_error(const femb200_assembler *ga, int32_t *kind, int64_t *elem, int32_t *qp) {
+  if (!ga) return FEMB200_ERR_BAD_ARG;
+  if (kind) *kind = ga->err_kind;
+  if (elem) *elem = ga->err_elem;
+  if (qp) *qp = ga->err_qp;
+  return 0;
+}
+
+int64_t femb200_total_dofs(const femb200_assembler *ga) { return ga ? ga->K.n_rows : 0; }
+int64_t femb200_nnz(const femb200_assembler *ga) { return ga ? ga->K.nnz : 0; }
+
+int femb200_csr_copy(const femb200_assembler *ga, int64_t *indptr, int32_t *indices, double *values) {
+  if (!ga) return FEMB200_ERR_BAD_ARG;
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const DeviceCsr &K = ga->K;
+  if (indptr) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(indptr, K.indptr, sizeof(int64_t) * (K.n_rows + 1), cudaMemcpyDeviceToHost, st));
+  if (indices && K.nnz) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(indices, K.indices, sizeof(int32_t) * K.nnz, cudaMemcpyDeviceToHost, st));
+  if (values && K.nnz) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(values, K.values, sizeof(double) * K.nnz, cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int femb200_csr_device(const femb200_assembler *ga, const int64_t **indptr, const int32_t **indices, const double **values) {
+  if (!ga) return FEMB200_ERR_BAD_ARG;
+  if (indptr) *indptr = ga->K.indptr;
+  if (indices) *indices = ga->K.indices;
+  if (values) *values = ga->K.values;
+  return 0;
+}
+
+__global__ void k_at(const int64_t *ptr, const int32_t *idx, const double *val, int64_t i, int32_t j, double *out) {
+  double v = 0.0;
+  int64_t lo = ptr[i], hi = ptr[i + 1];
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (idx[mid] < j) lo = mid + 1; else hi = mid;
+  }
+  if (lo < ptr[i + 1] && idx[lo] == j) v = val[lo];
+  *out = v;
+}
+
+int femb200_csr_at(const femb200_assembler *ga, int64_t i, int64_t j, double *out) {
+  if (!ga || !out || i < 0 || j < 0 || i >= ga->K.n_rows || j >= ga->K.n_rows) return FEMB200_ERR_BAD_ARG;
+  femb200_ctx *ctx = ga->ctx;
+  *out = 0.0;
+  if (ga->K.nnz == 0) return 0;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  double *d = (double *)ctx->d_scalars;
+  k_at<<<1, 1, 0, ctx->stream>>>(ga->K.indptr, ga->K.indices, ga->K.values, i, (int32_t)j, d);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out, ctx->h_scalars, sizeof(double));
+  return 0;
+}
+
+int femb200_csr_matvec(const femb200_assembler *cga, const double *x, double *y) {
+  femb200_assembler *ga = const_cast<femb200_assembler *>(cga);
+  if (!ga || !x || !y) return FEMB200_ERR_BAD_ARG;
+  femb200_ctx *ctx = ga->ctx;
+  const int64_t n = ga->K.n_rows;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  double *dx = nullptr, *dy = nullptr;
+  int rc;
+  if ((rc = dev_alloc(ctx, &dx, (size_t)n))) return rc;
+  if ((rc = dev_alloc(ctx, &dy, (size_t)n))) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = csr_matvec(ga, dx, dy);
+  if (!rc) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  dev_free(ctx, dx); dev_free(ctx, dy);
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+
+int femb200_last_slot_map(const femb200_assembler *cga, int64_t *slot) {
+  femb200_assembler *ga = const_cast<femb200_assembler *>(cga);
+  if (!ga || !slot || !ga->plan.n2e_t) return FEMB200_ERR_BAD_ARG;
+  femb200_ctx *ctx = ga->ctx;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ga->plan.n_elem * ga->plan.nn * ga->plan.nn;
+  int64_t *d = nullptr;
+  int rc;
+  if ((rc = dev_alloc(ctx, &d, n))) return rc;
+  rc = slot_map(ga, d);
+  if (!rc && n) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(slot, d, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  dev_free(ctx, d);
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+
+int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn,
+                                  int32_t conn_is_int64, int32_t conn_on_device, int64_t n_elem, const double *u,
+                                  double *strains) {
+  if (!ga || n_elem < 0 || !u || (n_elem > 0 && (!conn || !strains))) return FEMB200_ERR_BAD_ARG;
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  ga->err_kind = 0; ga->err_elem = -1; ga->err_qp = -1;
+  ElemShape sh;
+  std::vector<double> blob;
+  int rc = prepare(ga, desc, &sh, &blob);
+  if (rc) { ga->err_kind = rc; return rc; }
+  *ctx->h_err = kNoError;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+  int32_t *conn32 = nullptr, *d_dofmap = nullptr;
+  void *staged = nullptr;
+  double *d_tab = nullptr, *d_u = nullptr, *d_s = nullptr;
+  const int64_t ndof = ga->K.n_rows;
+  const size_t ns = (size_t)n_elem * sh.nqp * sh.dimC;
+  rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged);
+  if (!rc) rc = dev_alloc(ctx, &d_tab, blob.size());
+  if (!rc) rc = dev_alloc(ctx, &d_u, (size_t)ndof);
+  if (!rc) rc = dev_alloc(ctx, &d_s, ns);
+  if (!rc) rc = dev_alloc(ctx, &d_dofmap, kMaxNdn);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u, sizeof(double) * ndof, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_dofmap, desc->dofmap, sizeof(int32_t) * sh.ndn, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
+  }
+  if (!rc) rc = decode_error(ga); // out-of-range node ids
+  if (!rc) rc = strains_phase(ga, sh, d_tab, conn32, n_elem, d_dofmap, d_u, d_s);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && ns) e = cudaMemcpyAsync(strains, d_s, sizeof(double) * ns, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
+  }
+  if (!rc) rc = decode_error(ga);
+  dev_free(ctx, conn32); dev_free(ctx, d_tab); dev_free(ctx, d_u); dev_free(ctx, d_s); dev_free(ctx, d_dofmap);
+  if (staged) cudaFreeAsync(staged, st);
+  cudaStreamSynchronize(st);
+  if (rc) ga->err_kind = rc;
+  return rc;
+}
+
+int femb200_phase_ms(const femb200_assembler *ga, float out[FEMB200_N_TIMERS]) {
+  if (!ga || !out) return FEMB200_ERR_BAD_ARG;
+  for (int i = 0; i < FEMB200_N_TIMERS; ++i) out[i] = ga->phase_ms[i];
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,148 @@
+// common.cuh -- internal structures of libfemb200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/femb200.h"
+
+namespace femb200 {
+
+// ---- limits of the device tables -------------------------------------------------------------
+constexpr int kMaxNN = 20;       // Hexa20
+constexpr int kMaxD = 3;
+constexpr int kMaxNdn = 6;       // DofsFlag has 6 named bits (fem.go:70-82)
+constexpr int kMaxDimC = 6;
+constexpr int kTabDoubles = 5632; // 44 KB of __constant__ table space (N | dN | w | C)
+
+// Layout of the per-call table blob (doubles): [C dimC*dimC][w nqp][N nqp*nn][dN nqp*d*nn]
+struct TabLayout {
+  int offC, offW, offN, offDN, total;
+};
+inline TabLayout tab_layout(int d, int nn, int nqp, int dimC) {
+  TabLayout t;
+  t.offC = 0;
+  t.offW = dimC * dimC;
+  t.offN = t.offW + nqp;
+  t.offDN = t.offN + nqp * nn;
+  t.total = t.offDN + nqp * d * nn;
+  return t;
+}
+
+// Device error word: min over (elem << 16 | qp << 4 | kind) so the LOWEST failing element wins,
+// then its first failing quadrature point (sequential semantics of fem.go:140-151).
+constexpr unsigned long long kNoError = ~0ull;
+__host__ __device__ inline unsigned long long pack_error(long long elem, int qp, int kind) {
+  return ((unsigned long long)elem << 16) | ((unsigned long long)(qp & 0xfff) << 4) | (unsigned long long)(kind & 0xf);
+}
+
+struct DeviceCsr {
+  int64_t n_rows = 0;
+  int64_t nnz = 0;
+  int64_t *indptr = nullptr;  // [n_rows+1]
+  int32_t *indices = nullptr; // [nnz]
+  double *values = nullptr;   // [nnz]
+};
+
+// Per-call symbolic plan kept for the slot-map query.
+struct LastPlan {
+  int nn = 0, nu = 0;
+  int64_t n_elem = 0;
+  int32_t *n2e_ptr = nullptr;   // [n_nodes+1] incidence offsets
+  uint32_t *n2e_t = nullptr;    // [n_elem*nn] t = e*nn + a, grouped by node, ascending
+  uint16_t *pos16 = nullptr;    // [n_elem*nn][nn] row-local block position
+  int64_t *blkptr = nullptr;    // [n_nodes+1] node-block row offsets (of THIS call's pattern)
+};
+
+} // namespace femb200
+
+struct femb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaMemPool_t pool = nullptr;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  std::string last_cuda_error;
+  void *cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  unsigned long long *d_err = nullptr;      // device error word
+  int64_t *d_scalars = nullptr;             // small device scratch (8 x int64)
+  int64_t *h_scalars = nullptr;             // pinned host mirror
+  unsigned long long *h_err = nullptr;      // pinned
+  cudaEvent_t ev[10] = {};
+};
+
+struct femb200_assembler {
+  femb200_ctx *ctx = nullptr;
+  const double *d_nodes = nullptr; // [n_nodes][3]
+  bool own_nodes = true;
+  int64_t n_nodes = 0;
+  int32_t mdpn = 0;
+  femb200::DeviceCsr K;
+  femb200::LastPlan plan;
+  int32_t err_kind = 0;
+  int64_t err_elem = -1;
+  int32_t err_qp = -1;
+  float phase_ms[FEMB200_N_TIMERS] = {};
+};
+
+namespace femb200 {
+
+#define FEMB_CUDA_OK(ctx, expr)                                                         \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      (ctx)->last_cuda_error = std::string(#expr) + ": " + cudaGetErrorString(_e);      \
+      return FEMB200_ERR_CUDA;                                                          \
+    }                                                                                   \
+  } while (0)
+
+template <class T> inline int dev_alloc(femb200_ctx *ctx, T **p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  FEMB_CUDA_OK(ctx, cudaMallocAsync((void **)p, n * sizeof(T), ctx->pool, ctx->stream));
+  return 0;
+}
+template <class T> inline void dev_free(femb200_ctx *ctx, T *&p) {
+  if (p) cudaFreeAsync((void *)p, ctx->stream);
+  p = nullptr;
+}
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---- phases (symbolic.cu / numeric.cu / csr_ops.cu) -------------------------------------------
+struct ElemShape {
+  int d, nn, ndn, nqp, dimC, bkind;
+  int nu;                 // number of distinct dofmap values
+  int umap[kMaxNdn];      // sorted distinct dofmap values U
+  int dof2u[kMaxNdn];     // dofmap[i] -> index into U
+  bool identity;          // dofmap == [0..ndn) and nu == ndn == mdpn
+  int mdpn;
+};
+
+struct SymbolicResult {
+  int32_t *n2e_ptr = nullptr;
+  uint32_t *n2e_t = nullptr;
+  uint16_t *pos16 = nullptr;
+  int64_t *blkptr = nullptr;
+  int32_t *blkcols = nullptr;
+  int64_t nblk = 0;
+  int max_rowlen = 0;
+  DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)
+};
+
+// conn32: device [n_elem*nn] validated int32 connectivity.
+int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *conn32, int64_t n_elem,
+                   SymbolicResult *out);
+int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, int tab_doubles,
+                  const int32_t *conn32, int64_t n_elem, SymbolicResult *sym);
+bool numeric_supported(const ElemShape &sh);
+int csr_merge_into(femb200_assembler *ga, DeviceCsr *add); // K += add (consumes add)
+int csr_matvec(femb200_assembler *ga, const double *d_x, double *d_y);
+int strains_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32,
+                  int64_t n_elem, const int32_t *d_dofmap, const double *d_u, double *d_strains);
+int narrow_and_validate_conn(femb200_assembler *ga, const void *d_conn_in, bool is64, int64_t n, int nn,
+                             int32_t *conn32_out);
+int slot_map(femb200_assembler *ga, int64_t *d_slot);
+
+} // namespace femb200

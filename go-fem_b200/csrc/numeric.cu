@@ -1,0 +1,531 @@
+// numeric.cu -- numeric phase + deterministic row reduction, fused in ONE kernel.
+//
+// Reference semantics (assembler_isoparametric.go:85-117, per element, per quadrature point):
+//   jac = dN*X (:93); dJac = det(jac) with the <0 / <1e-12 checks (:94-99); dNxy = jac^-1 dN (:100);
+//   B filled by the constituter (:104, straindisplacement.go / thermal.go); Ke += B^T C B * dJac*w*scale (:109-112);
+//   then nd^2 COO triplets per element (assembler.go:79-92) summed by lap.Sparse.Accumulate (:121).
+//
+// B200 design: ROW-centric gather.  One thread owns one node-block row I of K.  It walks the elements
+// incident to node I in ascending element index (n2e lists of the symbolic phase), recomputes that
+// element's geometry in FP64 registers, forms only block-row a of Ke (a = local index of I in e):
+//     Ke[a][b] = sum_q (B_a^T C) B_b * dJac*w*scale      (ndn x ndn block, B sparsity exploited)
+// and adds it to the row's accumulators in shared memory (interleaved by thread => bank-conflict free).
+// No COO stream, no Ke staging in HBM, no atomics: every K entry is a fixed-order (ascending element)
+// sum, i.e. a deterministic segmented reduction whose segments are the CSR rows.  HBM traffic is the
+// compulsory one: connectivity + coordinates (L2 resident) in, CSR values out.
+#include "common.cuh"
+
+namespace femb200 {
+
+__constant__ double c_tab[kTabDoubles];
+
+// ---- strain-displacement block structure ---------------------------------------------------------
+// Node "values" v[] and the selector sel(k,i): B_node[k][i] = v[sel] (or 0 when sel < 0).
+//  XYZ            v = (gx, gy, gz)              straindisplacement.go:5-26
+//  PLANE          v = (gx, gy)                  straindisplacement.go:28-40
+//  AXISYM         v = (gr, gz, N/r)             straindisplacement.go:42-58
+//  THERMAL        v = (g0..g_{d-1})             thermal.go:18-21,31-34 (B = dN)
+//  THERMAL_AXISYM v = (N/r + gr, gz)            thermal.go:43-56
+template <int BKIND, int D> struct BT;
+template <> struct BT<FEMB200_B_XYZ, 3> {
+  static constexpr int NDN = 3, DIMC = 6, NV = 3; static constexpr bool RADIAL = false;
+  __host__ __device__ static constexpr int sel(int k, int i) {
+    constexpr int t[6][3] = {{0, -1, -1}, {-1, 1, -1}, {-1, -1, 2}, {1, 0, -1}, {-1, 2, 1}, {2, -1, 0}};
+    return t[k][i];
+  }
+};
+template <> struct BT<FEMB200_B_PLANE, 2> {
+  static constexpr int NDN = 2, DIMC = 3, NV = 2; static constexpr bool RADIAL = false;
+  __host__ __device__ static constexpr int sel(int k, int i) {
+    constexpr int t[3][2] = {{0, -1}, {-1, 1}, {1, 0}};
+    return t[k][i];
+  }
+};
+template <> struct BT<FEMB200_B_AXISYM, 2> {
+  static constexpr int NDN = 2, DIMC = 4, NV = 3; static constexpr bool RADIAL = true;
+  __host__ __device__ static constexpr int sel(int k, int i) {
+    constexpr int t[4][2] = {{0, -1}, {2, -1}, {-1, 1}, {1, 0}};
+    return t[k][i];
+  }
+};
+template <int D> struct BT<FEMB200_B_THERMAL, D> {
+  static constexpr int NDN = 1, DIMC = D, NV = D; static constexpr bool RADIAL = false;
+  __host__ __device__ static constexpr int sel(int k, int i) { return k; }
+};
+template <> struct BT<FEMB200_B_THERMAL_AXISYM, 2> {
+  static constexpr int NDN = 1, DIMC = 2, NV = 2; static constexpr bool RADIAL = true;
+  __host__ __device__ static constexpr int sel(int k, int i) { return k; }
+};
+
+// ---- table access: __constant__ (uniform broadcast) or global fallback for oversized tables -------
+template <bool TAB_CONST> struct Tab {
+  const double *g;
+  int offW, offN, offDN;
+  __device__ __forceinline__ double at(int i) const {
+    if constexpr (TAB_CONST) return c_tab[i]; else return __ldg(g + i);
+  }
+  template <int DIMC> __device__ __forceinline__ double C(int k, int c) const { return at(k * DIMC + c); }
+  __device__ __forceinline__ double w(int q) const { return at(offW + q); }
+  template <int NN> __device__ __forceinline__ double N(int q, int b) const { return at(offN + q * NN + b); }
+  template <int D, int NN> __device__ __forceinline__ double dN(int q, int i, int b) const { return at(offDN + (q * D + i) * NN + b); }
+};
+
+// ---- d x d inverse / determinant (closed form; the reference uses LU, differences are O(eps)) -----
+template <int D> __device__ __forceinline__ double inv_det(const double (&J)[D][D], double (&inv)[D][D]);
+template <> __device__ __forceinline__ double inv_det<1>(const double (&J)[1][1], double (&inv)[1][1]) {
+  inv[0][0] = 1.0 / J[0][0];
+  return J[0][0];
+}
+template <> __device__ __forceinline__ double inv_det<2>(const double (&J)[2][2], double (&inv)[2][2]) {
+  const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  const double r = 1.0 / det;
+  inv[0][0] = J[1][1] * r; inv[0][1] = -J[0][1] * r;
+  inv[1][0] = -J[1][0] * r; inv[1][1] = J[0][0] * r;
+  return det;
+}
+template <> __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&inv)[3][3]) {
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  const double r = 1.0 / det;
+  inv[0][0] = c00 * r; inv[1][0] = c01 * r; inv[2][0] = c02 * r;
+  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+  inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+  inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+  inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+  inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+  return det;
+}
+template <int D> __device__ __forceinline__ double norm1(const double (&A)[D][D]) {
+  double m = 0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += fabs(A[i][j]);
+    m = fmax(m, s);
+  }
+  return m;
+}
+
+// Geometry of one quadrature point.  Returns the error kind (0 = ok) exactly where the reference
+// would have returned it (assembler_isoparametric.go:95-107).
+template <int D, int NN, bool RADIAL, class TabT>
+__device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double (&X)[NN][D], double (&inv)[D][D],
+                                           double &detJ, double &rinv, double &scale) {
+  double J[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) J[i][j] = 0.0;
+#pragma unroll
+  for (int b = 0; b < NN; ++b)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double dn = tab.template dN<D, NN>(q, i, b);
+#pragma unroll
+      for (int j = 0; j < D; ++j) J[i][j] = fma(dn, X[b][j], J[i][j]);
+    }
+  detJ = inv_det<D>(J, inv);
+  if (detJ < 0) return FEMB200_ERR_NEG_DET;
+  if (detJ < 1e-12) return FEMB200_ERR_ZERO_DET;
+  if (norm1<D>(J) * norm1<D>(inv) > 1e16) return FEMB200_ERR_SOLVE;
+  scale = 1.0;
+  rinv = 0.0;
+  if constexpr (RADIAL) {
+    double r = 0.0;
+#pragma unroll
+    for (int b = 0; b < NN; ++b) r = fma(X[b][0], tab.template N<NN>(q, b), r);
+    rinv = 1.0 / r;
+    scale = r;
+    if (isnan(r)) return FEMB200_ERR_NAN_SCALE;
+  }
+  return 0;
+}
+
+// v[] of one node at quadrature point q (see BT above)
+template <int BKIND, int D, int NN, class TabT>
+__device__ __forceinline__ void node_vals(const TabT &tab, int q, int b, const double (&inv)[D][D], double rinv,
+                                          double (&v)[BT<BKIND, D>::NV]) {
+  double g[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) s = fma(inv[i][j], tab.template dN<D, NN>(q, j, b), s);
+    g[i] = s;
+  }
+  if constexpr (BKIND == FEMB200_B_AXISYM) {
+    v[0] = g[0]; v[1] = g[1]; v[2] = tab.template N<NN>(q, b) * rinv;
+  } else if constexpr (BKIND == FEMB200_B_THERMAL_AXISYM) {
+    v[0] = tab.template N<NN>(q, b) * rinv + g[0]; v[1] = g[1];
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = g[i];
+  }
+}
+
+// E = f * B_a^T C   (NDN x DIMC), only the structural non-zeros of B_a are touched
+template <int BKIND, int D, class TabT>
+__device__ __forceinline__ void bt_c(const TabT &tab, const double (&va)[BT<BKIND, D>::NV], double f,
+                                     double (&E)[BT<BKIND, D>::NDN][BT<BKIND, D>::DIMC]) {
+  using B = BT<BKIND, D>;
+  double vs[B::NV];
+#pragma unroll
+  for (int i = 0; i < B::NV; ++i) vs[i] = va[i] * f;
+#pragma unroll
+  for (int i = 0; i < B::NDN; ++i)
+#pragma unroll
+    for (int c = 0; c < B::DIMC; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < B::DIMC; ++k)
+        if (B::sel(k, i) >= 0) s = fma(vs[B::sel(k, i)], tab.template C<B::DIMC>(k, c), s);
+      E[i][c] = s;
+    }
+}
+
+// blk = E * B_b  (NDN x NDN)
+template <int BKIND, int D>
+__device__ __forceinline__ void e_b(const double (&E)[BT<BKIND, D>::NDN][BT<BKIND, D>::DIMC],
+                                    const double (&vb)[BT<BKIND, D>::NV],
+                                    double (&blk)[BT<BKIND, D>::NDN * BT<BKIND, D>::NDN]) {
+  using B = BT<BKIND, D>;
+#pragma unroll
+  for (int i = 0; i < B::NDN; ++i)
+#pragma unroll
+    for (int j = 0; j < B::NDN; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < B::DIMC; ++k)
+        if (B::sel(k, j) >= 0) s = fma(E[i][k], vb[B::sel(k, j)], s);
+      blk[i * B::NDN + j] = s;
+    }
+}
+
+struct NumArgs {
+  int64_t n_nodes;
+  const double *nodes;        // [n_nodes][3]
+  const int32_t *conn;        // [n_elem][NN]
+  const int32_t *n2e_ptr;     // [n_nodes+1]
+  const uint32_t *n2e_t;      // [n_elem*NN]
+  const uint16_t *pos16;      // [n_elem*NN][NN]
+  const int64_t *blkptr;      // [n_nodes+1]
+  double *values;             // CSR values of this call
+  unsigned long long *err;
+  const double *tab_g;
+  int offW, offN, offDN, nqp;
+  int nu;                     // distinct dofmap values (== NDN when identity)
+  int dof2u[kMaxNdn];
+};
+
+// SMEM_ACC: row accumulators in shared memory R[(p*NB2 + k)*T + tid] (requires identity dofmap);
+// otherwise they are the final CSR slots in global memory (pre-zeroed), which also handles the
+// reference's non-injective dofmap quirk (fem.go:155-172).
+// ACC_REGS: the whole block-row of one element is summed over quadrature points in registers first.
+template <int D, int NN, int BKIND, bool SMEM_ACC, bool ACC_REGS, bool TAB_CONST, int TPB>
+__global__ void __launch_bounds__(TPB)
+k_numeric_rows(const NumArgs a) {
+  using B = BT<BKIND, D>;
+  constexpr int NDN = B::NDN, NB2 = NDN * NDN, NV = B::NV;
+  extern __shared__ double s_R[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int64_t I = (int64_t)blockIdx.x * T + tid;
+  if (I >= a.n_nodes) return;
+  Tab<TAB_CONST> tab{a.tab_g, a.offW, a.offN, a.offDN};
+  const int beg = a.n2e_ptr[I], end = a.n2e_ptr[I + 1];
+  const int64_t b0 = a.blkptr[I];
+  const int rl = (int)(a.blkptr[I + 1] - b0);
+  const int nu = SMEM_ACC ? NDN : a.nu;
+  double *const vrow = a.values + (int64_t)nu * nu * b0; // this block row's slice of CSR values
+
+  if constexpr (SMEM_ACC) {
+    for (int m = 0; m < rl * NB2; ++m) s_R[m * T + tid] = 0.0;
+  }
+  auto add_block = [&](int p, const double(&blk)[NB2]) {
+    if constexpr (SMEM_ACC) {
+#pragma unroll
+      for (int k = 0; k < NB2; ++k) s_R[(p * NB2 + k) * T + tid] += blk[k];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NDN; ++i)
+#pragma unroll
+        for (int j = 0; j < NDN; ++j)
+          vrow[(int64_t)a.dof2u[i] * rl * nu + (int64_t)p * nu + a.dof2u[j]] += blk[i * NDN + j];
+    }
+  };
+
+  for (int k = beg; k < end; ++k) {
+    const uint32_t t = a.n2e_t[k];
+    const int64_t e = t / NN;
+    const int la = (int)(t % NN);
+    double X[NN][D];
+    {
+      const int32_t *ce = a.conn + e * NN;
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+        const int64_t nb = __ldg(ce + b);
+#pragma unroll
+        for (int j = 0; j < D; ++j) X[b][j] = __ldg(a.nodes + nb * 3 + j);
+      }
+    }
+    const uint16_t *pk = a.pos16 + (int64_t)k * NN;
+    double acc[ACC_REGS ? NN : 1][NB2];
+    if constexpr (ACC_REGS) {
+#pragma unroll
+      for (int b = 0; b < NN; ++b)
+#pragma unroll
+        for (int m = 0; m < NB2; ++m) acc[b][m] = 0.0;
+    }
+    bool bad = false;
+    for (int q = 0; q < a.nqp; ++q) {
+      double inv[D][D], detJ, rinv, scale;
+      const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
+      if (ek) {
+        atomicMin(a.err, pack_error(e, q, ek));
+        bad = true;
+        break;
+      }
+      const double f = detJ * tab.w(q) * scale; // (dJac*w)*scale, left to right (:111)
+      double va[NV], E[NDN][B::DIMC];
+      node_vals<BKIND, D, NN>(tab, q, la, inv, rinv, va);
+      bt_c<BKIND, D>(tab, va, f, E);
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+        double vb[NV], blk[NB2];
+        node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+        e_b<BKIND, D>(E, vb, blk);
+        if constexpr (ACC_REGS) {
+#pragma unroll
+          for (int m = 0; m < NB2; ++m) acc[b][m] += blk[m];
+        } else {
+          add_block(pk[b], blk);
+        }
+      }
+    }
+    if constexpr (ACC_REGS) {
+      if (!bad) {
+#pragma unroll
+        for (int b = 0; b < NN; ++b) add_block(pk[b], acc[b]);
+      }
+    }
+  }
+
+  if constexpr (SMEM_ACC) {
+    // scalar CSR layout of the block row: scalar row i holds rl*NDN entries, entry (p, j) at p*NDN + j
+    for (int i = 0; i < NDN; ++i)
+      for (int p = 0; p < rl; ++p)
+#pragma unroll
+        for (int j = 0; j < NDN; ++j)
+          vrow[(int64_t)i * rl * NDN + p * NDN + j] = s_R[(p * NB2 + i * NDN + j) * T + tid];
+  }
+}
+
+// ---- launch plumbing -------------------------------------------------------------------------------
+template <int D, int NN, int BKIND, bool SMEM_ACC, bool TAB_CONST>
+static int launch_rows_T(femb200_ctx *ctx, const NumArgs &a, int max_rowlen) {
+  using B = BT<BKIND, D>;
+  constexpr int NB2 = B::NDN * B::NDN;
+  constexpr bool ACC_REGS = (NN * NB2 <= 36);
+  constexpr int TPB = 128;
+  auto kern = k_numeric_rows<D, NN, BKIND, SMEM_ACC, ACC_REGS, TAB_CONST, TPB>;
+  int T = TPB;
+  size_t smem = 0;
+  if (SMEM_ACC) {
+    const size_t per_thread = (size_t)max_rowlen * NB2 * sizeof(double);
+    FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    int best_threads = 0, bestT = 0;
+    const int cands[4] = {128, 96, 64, 32};
+    for (int c = 0; c < 4; ++c) {
+      size_t need = per_thread * cands[c];
+      if (need > ctx->smem_optin) continue;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, cands[c], need) != cudaSuccess) continue;
+      if (nb * cands[c] > best_threads) { best_threads = nb * cands[c]; bestT = cands[c]; }
+    }
+    if (bestT == 0) return -2; // does not fit: caller falls back to global accumulators
+    T = bestT;
+    smem = per_thread * T;
+  }
+  kern<<<grid_for(a.n_nodes, T), T, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+template <int D, int NN, int BKIND>
+static int launch_rows(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, bool tab_const, SymbolicResult *sym) {
+  femb200_ctx *ctx = ga->ctx;
+  using B = BT<BKIND, D>;
+  if (sh.ndn != B::NDN || sh.dimC != B::DIMC) return FEMB200_ERR_UNSUPPORTED;
+  int rc = -2;
+  const bool force_global = getenv("FEMB200_FORCE_GLOBAL_ACC") != nullptr;
+  if (sh.identity && !force_global)
+    rc = tab_const ? launch_rows_T<D, NN, BKIND, true, true>(ctx, a, sym->max_rowlen)
+                   : launch_rows_T<D, NN, BKIND, true, false>(ctx, a, sym->max_rowlen);
+  if (rc == -2) {
+    FEMB_CUDA_OK(ctx, cudaMemsetAsync(a.values, 0, sizeof(double) * (size_t)sym->csr.nnz, ctx->stream));
+    rc = tab_const ? launch_rows_T<D, NN, BKIND, false, true>(ctx, a, sym->max_rowlen)
+                   : launch_rows_T<D, NN, BKIND, false, false>(ctx, a, sym->max_rowlen);
+  }
+  return rc;
+}
+
+template <int D, int BKIND>
+static int dispatch_nn(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, bool tc, SymbolicResult *sym) {
+  if (D == 3) {
+    switch (sh.nn) {
+    case 4: return launch_rows<D, 4, BKIND>(ga, sh, a, tc, sym);
+    case 8: return launch_rows<D, 8, BKIND>(ga, sh, a, tc, sym);
+    case 10: return launch_rows<D, 10, BKIND>(ga, sh, a, tc, sym);
+    case 20: return launch_rows<D, 20, BKIND>(ga, sh, a, tc, sym);
+    }
+  } else {
+    switch (sh.nn) {
+    case 3: return launch_rows<D, 3, BKIND>(ga, sh, a, tc, sym);
+    case 4: return launch_rows<D, 4, BKIND>(ga, sh, a, tc, sym);
+    case 8: return launch_rows<D, 8, BKIND>(ga, sh, a, tc, sym);
+    }
+  }
+  return FEMB200_ERR_UNSUPPORTED;
+}
+
+bool numeric_supported(const ElemShape &sh) {
+  const bool nn3 = sh.nn == 4 || sh.nn == 8 || sh.nn == 10 || sh.nn == 20;
+  const bool nn2 = sh.nn == 3 || sh.nn == 4 || sh.nn == 8;
+  switch (sh.bkind) {
+  case FEMB200_B_XYZ: return sh.d == 3 && sh.ndn == 3 && sh.dimC == 6 && nn3;
+  case FEMB200_B_PLANE: return sh.d == 2 && sh.ndn == 2 && sh.dimC == 3 && nn2;
+  case FEMB200_B_AXISYM: return sh.d == 2 && sh.ndn == 2 && sh.dimC == 4 && nn2;
+  case FEMB200_B_THERMAL: return sh.ndn == 1 && sh.dimC == sh.d && ((sh.d == 3 && nn3) || (sh.d == 2 && nn2));
+  case FEMB200_B_THERMAL_AXISYM: return sh.d == 2 && sh.ndn == 1 && sh.dimC == 2 && nn2;
+  }
+  return false;
+}
+
+int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, int tab_doubles,
+                  const int32_t *conn32, int64_t n_elem, SymbolicResult *sym) {
+  femb200_ctx *ctx = ga->ctx;
+  if (!numeric_supported(sh)) return FEMB200_ERR_UNSUPPORTED;
+  const bool tab_const = tab_doubles <= kTabDoubles;
+  if (tab_const)
+    FEMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_tab, h_tab, sizeof(double) * tab_doubles, 0, cudaMemcpyHostToDevice, ctx->stream));
+  TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
+  NumArgs a;
+  a.n_nodes = ga->n_nodes;
+  a.nodes = ga->d_nodes;
+  a.conn = conn32;
+  a.n2e_ptr = sym->n2e_ptr;
+  a.n2e_t = sym->n2e_t;
+  a.pos16 = sym->pos16;
+  a.blkptr = sym->blkptr;
+  a.values = sym->csr.values;
+  a.err = ctx->d_err;
+  a.tab_g = d_tab;
+  a.offW = tl.offW; a.offN = tl.offN; a.offDN = tl.offDN; a.nqp = sh.nqp;
+  a.nu = sh.nu;
+  for (int i = 0; i < kMaxNdn; ++i) a.dof2u[i] = sh.dof2u[i];
+  switch (sh.bkind) {
+  case FEMB200_B_XYZ: return dispatch_nn<3, FEMB200_B_XYZ>(ga, sh, a, tab_const, sym);
+  case FEMB200_B_PLANE: return dispatch_nn<2, FEMB200_B_PLANE>(ga, sh, a, tab_const, sym);
+  case FEMB200_B_AXISYM: return dispatch_nn<2, FEMB200_B_AXISYM>(ga, sh, a, tab_const, sym);
+  case FEMB200_B_THERMAL:
+    return sh.d == 3 ? dispatch_nn<3, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym)
+                     : dispatch_nn<2, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym);
+  case FEMB200_B_THERMAL_AXISYM: return dispatch_nn<2, FEMB200_B_THERMAL_AXISYM>(ga, sh, a, tab_const, sym);
+  }
+  return FEMB200_ERR_UNSUPPORTED;
+}
+
+// ---- IsoparametricStrains (assembler_isoparametric.go:126-213): one thread per element -----------
+template <int D, int NN, int BKIND, bool TAB_CONST>
+__global__ void k_strains(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__restrict__ conn,
+                          const double *__restrict__ u, double *__restrict__ strains, unsigned long long *err,
+                          const double *tab_g, int offW, int offN, int offDN, int nqp, int mdpn,
+                          const int32_t *__restrict__ dofmap) {
+  using B = BT<BKIND, D>;
+  constexpr int NDN = B::NDN, NV = B::NV, DIMC = B::DIMC;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  Tab<TAB_CONST> tab{tab_g, offW, offN, offDN};
+  double X[NN][D];
+  int64_t nd[NN];
+#pragma unroll
+  for (int b = 0; b < NN; ++b) {
+    nd[b] = conn[e * NN + b];
+#pragma unroll
+    for (int j = 0; j < D; ++j) X[b][j] = nodes[nd[b] * 3 + j];
+  }
+  for (int q = 0; q < nqp; ++q) {
+    double inv[D][D], detJ, rinv, scale;
+    const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
+    if (ek) { atomicMin(err, pack_error(e, q, ek)); return; }
+    double s[DIMC];
+#pragma unroll
+    for (int k = 0; k < DIMC; ++k) s[k] = 0.0;
+#pragma unroll
+    for (int b = 0; b < NN; ++b) {
+      double vb[NV];
+      node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+#pragma unroll
+      for (int i = 0; i < NDN; ++i) {
+        const double ui = u[nd[b] * mdpn + dofmap[i]];
+#pragma unroll
+        for (int k = 0; k < DIMC; ++k)
+          if (B::sel(k, i) >= 0) s[k] = fma(vb[B::sel(k, i)], ui, s[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DIMC; ++k) strains[(e * nqp + q) * DIMC + k] = s[k];
+  }
+}
+
+template <int D, int NN, int BKIND>
+static int launch_strains(femb200_ctx *ctx, bool tc, int64_t n_elem, const double *nodes, const int32_t *conn,
+                          const double *u, double *strains, const double *tab_g, const TabLayout &tl, int nqp, int mdpn,
+                          const int32_t *dofmap) {
+  if (n_elem == 0) return 0;
+  if (tc)
+    k_strains<D, NN, BKIND, true><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, nodes, conn, u, strains, ctx->d_err, tab_g, tl.offW, tl.offN, tl.offDN, nqp, mdpn, dofmap);
+  else
+    k_strains<D, NN, BKIND, false><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, nodes, conn, u, strains, ctx->d_err, tab_g, tl.offW, tl.offN, tl.offDN, nqp, mdpn, dofmap);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+template <int D, int BKIND>
+static int strains_nn(femb200_ctx *ctx, const ElemShape &sh, bool tc, int64_t n_elem, const double *nodes, const int32_t *conn,
+                      const double *u, double *strains, const double *tab_g, const TabLayout &tl, const int32_t *dofmap) {
+#define FEMB_S(NNV) return launch_strains<D, NNV, BKIND>(ctx, tc, n_elem, nodes, conn, u, strains, tab_g, tl, sh.nqp, sh.mdpn, dofmap)
+  if (D == 3) {
+    switch (sh.nn) { case 4: FEMB_S(4); case 8: FEMB_S(8); case 10: FEMB_S(10); case 20: FEMB_S(20); }
+  } else {
+    switch (sh.nn) { case 3: FEMB_S(3); case 4: FEMB_S(4); case 8: FEMB_S(8); }
+  }
+#undef FEMB_S
+  return FEMB200_ERR_UNSUPPORTED;
+}
+
+int strains_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32,
+                  int64_t n_elem, const int32_t *d_dofmap, const double *d_u, double *d_strains) {
+  femb200_ctx *ctx = ga->ctx;
+  if (!numeric_supported(sh)) return FEMB200_ERR_UNSUPPORTED;
+  TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
+  // strains always read the tables from global memory (tiny kernel, keeps c_tab free for assembly)
+  const bool tc = false;
+  switch (sh.bkind) {
+  case FEMB200_B_XYZ: return strains_nn<3, FEMB200_B_XYZ>(ctx, sh, tc, n_elem, ga->d_nodes, conn32, d_u, d_strains, d_tab, tl, d_dofmap);
+  case FEMB200_B_PLANE: return strains_nn<2, FEMB200_B_PLANE>(ctx, sh, tc, n_elem, ga->d_nodes, conn32, d_u, d_strains, d_tab, tl, d_dofmap);
+  case FEMB200_B_AXISYM: return strains_nn<2, FEMB200_B_AXISYM>(ctx, sh, tc, n_elem, ga->d_nodes, conn32, d_u, d_strains, d_tab, tl, d_dofmap);
+  case FEMB200_B_THERMAL:
+    return sh.d == 3 ? strains_nn<3, FEMB200_B_THERMAL>(ctx, sh, tc, n_elem, ga->d_nodes, conn32, d_u, d_strains, d_tab, tl, d_dofmap)
+                     : strains_nn<2, FEMB200_B_THERMAL>(ctx, sh, tc, n_elem, ga->d_nodes, conn32, d_u, d_strains, d_tab, tl, d_dofmap);
+  case FEMB200_B_THERMAL_AXISYM: return strains_nn<2, FEMB200_B_THERMAL_AXISYM>(ctx, sh, tc, n_elem, ga->d_nodes, conn32, d_u, d_strains, d_tab, tl, d_dofmap);
+  }
+  return FEMB200_ERR_UNSUPPORTED;
+}
+
+} // namespace femb200

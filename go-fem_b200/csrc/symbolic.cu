@@ -1,0 +1,319 @@
+// symbolic.cu -- on-device symbolic phase: node->element adjacency, node-block row pattern,
+// row-local slot positions and the scalar CSR pattern (indptr / indices).
+//
+// Replaces, for the whole call, what the reference does implicitly by emitting nd^2 COO triplets per
+// element (assembler.go:79-92) and letting lap.Sparse.Accumulate merge duplicates
+// (assembler_isoparametric.go:78-79,121).  Nothing is emitted per dof pair here: the pattern is built at
+// NODE-BLOCK granularity (nn^2 pairs per element instead of nd^2) and expanded once.
+//
+//   conn[e][a]                      --histogram+scan-->  n2e_ptr[node]
+//   (key=node, val=t=e*nn+a)        --radix sort----->   n2e_t grouped by node, t ascending (stable)
+//   per row node I                  --sorted insert-->   column nodes of row I (ascending), rowlen[I]
+//   second sweep over the incidences ---------------->   pos16[k][b] = position of node b of e in row I
+//   scan(rowlen) -> blkptr;  expand -> indptr (int64), indices (int32)
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace femb200 {
+
+// ------------------------------------------------------------------------------------------------
+template <class IntT>
+__global__ void k_narrow_validate(const IntT *__restrict__ in, int32_t *__restrict__ out, int64_t n, int nn,
+                                  int64_t n_nodes, unsigned long long *err) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  long long v = (long long)in[t];
+  if (v < 0 || v >= n_nodes) {
+    atomicMin(err, pack_error(t / nn, 0, FEMB200_ERR_NODE_OOB));
+    v = 0;
+  }
+  out[t] = (int32_t)v;
+}
+
+int narrow_and_validate_conn(femb200_assembler *ga, const void *d_in, bool is64, int64_t n, int nn, int32_t *out) {
+  femb200_ctx *ctx = ga->ctx;
+  if (n == 0) return 0;
+  if (is64)
+    k_narrow_validate<long long><<<grid_for(n, 256), 256, 0, ctx->stream>>>((const long long *)d_in, out, n, nn, ga->n_nodes, ctx->d_err);
+  else
+    k_narrow_validate<int32_t><<<grid_for(n, 256), 256, 0, ctx->stream>>>((const int32_t *)d_in, out, n, nn, ga->n_nodes, ctx->d_err);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_count_incidence(const int32_t *__restrict__ conn, int64_t n, int32_t *__restrict__ cnt,
+                                  uint32_t *__restrict__ iota) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  atomicAdd(&cnt[conn[t]], 1);
+  iota[t] = (uint32_t)t;
+}
+
+// One thread per row node: builds the ascending list of distinct column nodes of the node-block row.
+// The working list lives in shared memory, interleaved by thread (conflict free), and spills to the
+// thread's private slice of `tmpcols` (capacity nn * valence >= any possible row length) on overflow.
+template <int NN>
+__global__ void __launch_bounds__(128)
+k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, const uint32_t *__restrict__ n2e_t,
+              const int32_t *__restrict__ conn, int32_t *__restrict__ tmpcols, int64_t *__restrict__ rowlen,
+              uint16_t *__restrict__ pos16, int cap_s, unsigned long long *err) {
+  extern __shared__ int32_t s_list[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  int64_t I = (int64_t)blockIdx.x * T + tid;
+  if (I >= n_nodes) return;
+  const int beg = n2e_ptr[I], end = n2e_ptr[I + 1];
+  int32_t *gl = tmpcols + (int64_t)NN * beg;
+  bool in_s = true;
+  int cnt = 0;
+#define LST(i) (in_s ? s_list[(i) * T + tid] : gl[(i)])
+#define LST_SET(i, v)                                   \
+  do {                                                  \
+    if (in_s) s_list[(i) * T + tid] = (v); else gl[(i)] = (v); \
+  } while (0)
+  for (int k = beg; k < end; ++k) {
+    const int64_t e = n2e_t[k] / NN;
+    for (int b = 0; b < NN; ++b) {
+      const int32_t J = conn[e * NN + b];
+      int lo = 0, hi = cnt;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (LST(mid) < J) lo = mid + 1; else hi = mid;
+      }
+      if (lo < cnt && LST(lo) == J) continue;
+      if (in_s && cnt == cap_s) { // spill the shared list to the global slice and continue there
+        for (int m = 0; m < cnt; ++m) gl[m] = s_list[m * T + tid];
+        in_s = false;
+      }
+      for (int m = cnt; m > lo; --m) LST_SET(m, LST(m - 1));
+      LST_SET(lo, J);
+      ++cnt;
+    }
+  }
+  if (in_s) for (int m = 0; m < cnt; ++m) gl[m] = s_list[m * T + tid];
+  rowlen[I] = cnt;
+  // second sweep: row-local position of every (incidence, local node) = the element->slot map
+  for (int k = beg; k < end; ++k) {
+    const int64_t e = n2e_t[k] / NN;
+    for (int b = 0; b < NN; ++b) {
+      const int32_t J = conn[e * NN + b];
+      int lo = 0, hi = cnt;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (LST(mid) < J) lo = mid + 1; else hi = mid;
+      }
+      pos16[(int64_t)k * NN + b] = (uint16_t)lo;
+    }
+  }
+#undef LST
+#undef LST_SET
+}
+
+// scalar row pointers: row (I, m), m in [0, mdpn)
+__global__ void k_indptr(int64_t n_nodes, int mdpn, int nu, unsigned umask, const int64_t *__restrict__ blkptr,
+                         int64_t *__restrict__ indptr) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t ndof = n_nodes * mdpn;
+  if (r > ndof) return;
+  if (r == ndof) { indptr[r] = (int64_t)nu * nu * blkptr[n_nodes]; return; }
+  int64_t I = r / mdpn;
+  int m = (int)(r % mdpn);
+  int before = __popc(umask & ((1u << m) - 1u));
+  int64_t rl = blkptr[I + 1] - blkptr[I];
+  indptr[r] = (int64_t)nu * nu * blkptr[I] + (int64_t)before * rl * nu;
+}
+
+// one thread per node block g: finds its row by binary search on blkptr, compacts the column node and
+// writes the nu x nu scalar column indices (consecutive threads -> consecutive nu-int groups).
+__global__ void k_expand(int64_t n_nodes, int64_t nblk, int nn, int mdpn, int nu, const int *__restrict__ umap_packed,
+                         const int32_t *__restrict__ n2e_ptr, const int64_t *__restrict__ blkptr,
+                         const int32_t *__restrict__ tmpcols, int32_t *__restrict__ blkcols, int32_t *__restrict__ indices) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nblk) return;
+  int64_t lo = 0, hi = n_nodes; // largest I with blkptr[I] <= g
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (blkptr[mid] <= g) lo = mid; else hi = mid;
+  }
+  const int64_t I = lo;
+  const int64_t b0 = blkptr[I];
+  const int p = (int)(g - b0);
+  const int64_t rl = blkptr[I + 1] - b0;
+  const int32_t J = tmpcols[(int64_t)nn * n2e_ptr[I] + p];
+  blkcols[g] = J;
+  const int64_t base = (int64_t)nu * nu * b0;
+  for (int ur = 0; ur < nu; ++ur)
+    for (int uc = 0; uc < nu; ++uc)
+      indices[base + (int64_t)ur * rl * nu + (int64_t)p * nu + uc] = J * mdpn + umap_packed[uc];
+}
+
+template <int NN>
+static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *n2e_ptr, const uint32_t *n2e_t,
+                              const int32_t *conn, int32_t *tmpcols, int64_t *rowlen, uint16_t *pos16) {
+  const int T = 128;
+  // room for the longest rows of structured meshes (Hexa20 corner rows have 81 blocks)
+  int cap_s = NN <= 4 ? 48 : (NN <= 8 ? 64 : 96);
+  size_t smem = (size_t)cap_s * T * sizeof(int32_t);
+  FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(k_row_pattern<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_row_pattern<NN><<<grid_for(n_nodes, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, cap_s, ctx->d_err);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+static int ensure_cub_tmp(femb200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->cub_tmp_bytes) return 0;
+  if (ctx->cub_tmp) cudaFreeAsync(ctx->cub_tmp, ctx->stream);
+  ctx->cub_tmp = nullptr;
+  ctx->cub_tmp_bytes = 0;
+  FEMB_CUDA_OK(ctx, cudaMallocAsync(&ctx->cub_tmp, bytes, ctx->pool, ctx->stream));
+  ctx->cub_tmp_bytes = bytes;
+  return 0;
+}
+
+int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *conn32, int64_t n_elem,
+                   SymbolicResult *out) {
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  const int nn = sh.nn;
+  const int64_t n_nodes = ga->n_nodes;
+  const int64_t ninc = n_elem * nn;
+  if (ninc >= (int64_t)1 << 31 || n_nodes >= ((int64_t)1 << 31) / (sh.mdpn > 0 ? sh.mdpn : 1)) return FEMB200_ERR_TOO_LARGE;
+  int rc;
+
+  // ---- node -> element adjacency -------------------------------------------------------------
+  int32_t *cnt = nullptr;
+  uint32_t *iota = nullptr, *keys_sorted = nullptr;
+  if ((rc = dev_alloc(ctx, &cnt, n_nodes + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &iota, ninc))) return rc;
+  if ((rc = dev_alloc(ctx, &keys_sorted, ninc))) return rc;
+  if ((rc = dev_alloc(ctx, &out->n2e_ptr, n_nodes + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &out->n2e_t, ninc))) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (n_nodes + 1), st));
+  if (ninc) {
+    k_count_incidence<<<grid_for(ninc, 256), 256, 0, st>>>(conn32, ninc, cnt, iota);
+    ctx->launches++;
+  }
+  size_t tmp1 = 0, tmp2 = 0, tmp3 = 0, tmp4 = 0;
+  int end_bit = 1;
+  while (((int64_t)1 << end_bit) < n_nodes && end_bit < 32) ++end_bit;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp1, cnt, out->n2e_ptr, (int)(n_nodes + 1), st);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (const uint32_t *)conn32, keys_sorted, iota, out->n2e_t, (int)ninc, 0, end_bit, st);
+  int64_t *rowlen = nullptr;
+  if ((rc = dev_alloc(ctx, &rowlen, n_nodes + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &out->blkptr, n_nodes + 1))) return rc;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp3, rowlen, out->blkptr, (int)(n_nodes + 1), st);
+  cub::DeviceReduce::Max(nullptr, tmp4, rowlen, ctx->d_scalars, (int)(n_nodes + 1), st);
+  size_t tmpmax = tmp1 > tmp2 ? tmp1 : tmp2;
+  if (tmp3 > tmpmax) tmpmax = tmp3;
+  if (tmp4 > tmpmax) tmpmax = tmp4;
+  if ((rc = ensure_cub_tmp(ctx, tmpmax + 256))) return rc;
+  size_t tb = ctx->cub_tmp_bytes;
+  FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, cnt, out->n2e_ptr, (int)(n_nodes + 1), st));
+  ctx->launches += 2;
+  if (ninc) {
+    tb = ctx->cub_tmp_bytes;
+    FEMB_CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tb, (const uint32_t *)conn32, keys_sorted, iota, out->n2e_t, (int)ninc, 0, end_bit, st));
+    ctx->launches += 1 + 2 * ((end_bit + 7) / 8);
+  }
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], st));
+
+  // ---- node-block row pattern ----------------------------------------------------------------
+  int32_t *tmpcols = nullptr;
+  if ((rc = dev_alloc(ctx, &tmpcols, ninc * nn))) return rc;
+  if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn))) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(rowlen + n_nodes, 0, sizeof(int64_t), st));
+  switch (nn) {
+  case 3: rc = launch_row_pattern<3>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
+  case 4: rc = launch_row_pattern<4>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
+  case 8: rc = launch_row_pattern<8>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
+  case 10: rc = launch_row_pattern<10>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
+  case 20: rc = launch_row_pattern<20>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
+  default: rc = FEMB200_ERR_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  tb = ctx->cub_tmp_bytes;
+  FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, rowlen, out->blkptr, (int)(n_nodes + 1), st));
+  tb = ctx->cub_tmp_bytes;
+  FEMB_CUDA_OK(ctx, cub::DeviceReduce::Max(ctx->cub_tmp, tb, rowlen, ctx->d_scalars, (int)(n_nodes + 1), st));
+  ctx->launches += 4;
+  // host needs nblk (allocation sizes), max row length (numeric launch shape) and the error word
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 1, out->blkptr + n_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  out->max_rowlen = (int)ctx->h_scalars[0];
+  out->nblk = ctx->h_scalars[1];
+  dev_free(ctx, cnt);
+  dev_free(ctx, iota);
+  dev_free(ctx, keys_sorted);
+  dev_free(ctx, rowlen);
+  if (*ctx->h_err != kNoError) { dev_free(ctx, tmpcols); return -1; } // caller decodes the error word
+  if (out->max_rowlen > 65535) { dev_free(ctx, tmpcols); return FEMB200_ERR_TOO_LARGE; }
+
+  // ---- scalar CSR pattern ----------------------------------------------------------------------
+  const int nu = sh.nu;
+  const int64_t nnz = (int64_t)nu * nu * out->nblk;
+  const int64_t ndof = n_nodes * sh.mdpn;
+  if ((int64_t)out->max_rowlen * nu >= ((int64_t)1 << 31)) { dev_free(ctx, tmpcols); return FEMB200_ERR_TOO_LARGE; }
+  out->csr.n_rows = ndof;
+  out->csr.nnz = nnz;
+  if ((rc = dev_alloc(ctx, &out->csr.indptr, ndof + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &out->csr.indices, nnz))) return rc;
+  if ((rc = dev_alloc(ctx, &out->csr.values, nnz))) return rc;
+  if ((rc = dev_alloc(ctx, &out->blkcols, out->nblk))) return rc;
+  unsigned umask = 0;
+  for (int i = 0; i < nu; ++i) umask |= 1u << sh.umap[i];
+  int *d_umap = nullptr;
+  if ((rc = dev_alloc(ctx, &d_umap, kMaxNdn))) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_umap, sh.umap, sizeof(int) * kMaxNdn, cudaMemcpyHostToDevice, st));
+  k_indptr<<<grid_for(ndof + 1, 256), 256, 0, st>>>(n_nodes, sh.mdpn, nu, umask, out->blkptr, out->csr.indptr);
+  ctx->launches++;
+  if (out->nblk) {
+    k_expand<<<grid_for(out->nblk, 256), 256, 0, st>>>(n_nodes, out->nblk, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->blkcols, out->csr.indices);
+    ctx->launches++;
+  }
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  dev_free(ctx, d_umap);
+  dev_free(ctx, tmpcols);
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element -> slot map query (north_star subsystem 1): slot[e][a][b] = blkptr[node_a] + pos16
+__global__ void k_slot_map(int64_t ninc, int nn, const int32_t *__restrict__ n2e_ptr_unused, const uint32_t *__restrict__ n2e_t,
+                           const uint16_t *__restrict__ pos16, const int64_t *__restrict__ blkptr,
+                           const int32_t *__restrict__ node_of_k, int64_t *__restrict__ slot) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ninc) return;
+  const uint32_t t = n2e_t[k]; // = e*nn + a
+  const int64_t base = blkptr[node_of_k[k]];
+  for (int b = 0; b < nn; ++b) slot[(int64_t)t * nn + b] = base + pos16[k * nn + b];
+}
+
+__global__ void k_node_of_k(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, int32_t *__restrict__ node_of_k) {
+  int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= n_nodes) return;
+  for (int k = n2e_ptr[I]; k < n2e_ptr[I + 1]; ++k) node_of_k[k] = (int32_t)I;
+}
+
+int slot_map(femb200_assembler *ga, int64_t *d_slot) {
+  femb200_ctx *ctx = ga->ctx;
+  LastPlan &pl = ga->plan;
+  if (!pl.n2e_t) return FEMB200_ERR_BAD_ARG;
+  const int64_t ninc = pl.n_elem * pl.nn;
+  int32_t *node_of_k = nullptr;
+  int rc;
+  if ((rc = dev_alloc(ctx, &node_of_k, ninc))) return rc;
+  k_node_of_k<<<grid_for(ga->n_nodes, 256), 256, 0, ctx->stream>>>(ga->n_nodes, pl.n2e_ptr, node_of_k);
+  if (ninc) k_slot_map<<<grid_for(ninc, 256), 256, 0, ctx->stream>>>(ninc, pl.nn, pl.n2e_ptr, pl.n2e_t, pl.pos16, pl.blkptr, node_of_k, d_slot);
+  ctx->launches += 2;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  dev_free(ctx, node_of_k);
+  return 0;
+}
+
+} // namespace femb200

@@ -1,0 +1,144 @@
+/*
+ * femb200.h -- C ABI of libfemb200.so: B200 (sm_100a) isoparametric stiffness assembly.
+ *
+ * This is the drop-in boundary for ONE path of soypat/go-fem:
+ *     fem.NewGeneralAssembler -> (*GeneralAssembler).AddIsoparametric -> Ksolid
+ * Each entry point names the reference interface it replaces (paths relative to the go-fem tree).
+ * The Go side binds these with cgo; only plain pointers and sizes cross.
+ *
+ * Ownership: the caller owns every input buffer and it is only read during the call (cgo rule:
+ * Go memory is never retained).  The library owns all device memory and the CSR until *_destroy.
+ * Threading: one context per OS thread / assembler; calls on one assembler are serialised by the
+ * caller, exactly like the reference (GeneralAssembler has no locks, assembler.go:13-18).
+ * There is NO CPU fallback: every call fails with FEMB200_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef FEMB200_H
+#define FEMB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEMB200_ABI_VERSION 1
+
+/* Strain-displacement layouts = the fillers of constitution/solids/straindisplacement.go:5-58 and
+ * thermal.go:16-58.  The Go `solids` package tags its constituter with one of these
+ * (solids.isoconstituter is unexported, solids.go:8-12, so the kind cannot be discovered otherwise). */
+enum femb200_bkind {
+  FEMB200_B_XYZ = 0,            /* SetStrainDisplacementMatrixXYZ          d=3 ndn=3 dimC=6 */
+  FEMB200_B_PLANE = 1,          /* SetStrainDisplacementMatrixPlane        d=2 ndn=2 dimC=3 */
+  FEMB200_B_AXISYM = 2,         /* SetStrainDisplacementMatrixAxisymmetric d=2 ndn=2 dimC=4, scale=r */
+  FEMB200_B_THERMAL = 3,        /* thermal.go:18-21,31-34  B=dN            ndn=1 dimC=d */
+  FEMB200_B_THERMAL_AXISYM = 4  /* thermal.go:43-56                        d=2 ndn=1 dimC=2, scale=r */
+};
+
+/* Status codes.  1..4 are the per-element errors of assembler_isoparametric.go:95-107; the Go shim
+ * formats the reference's exact message from (kind, elem, qp) -- see femb200_last_error. */
+enum femb200_status {
+  FEMB200_OK = 0,
+  FEMB200_ERR_NEG_DET = 1,      /* :96  negative determinant of jacobian of element #%d */
+  FEMB200_ERR_ZERO_DET = 2,     /* :98  zero determinant (dJac < 1e-12, absolute) */
+  FEMB200_ERR_SOLVE = 3,        /* :102 form factor solve: cond_1(J) > 1e16 (mat.ConditionTolerance) */
+  FEMB200_ERR_NAN_SCALE = 4,    /* :106 NaN scale returned by SetStrainDisplacementMatrix */
+  FEMB200_ERR_NODE_OOB = 8,     /* node index outside [0, n_nodes): Go slice-bounds panic, assembler.go:137 */
+  FEMB200_ERR_BAD_ARG = 20,     /* malformed descriptor (nil pointers, sizes out of range) */
+  FEMB200_ERR_UNSUPPORTED = 21, /* (d, nn, ndn, dimC, bkind) combination with no compiled kernel */
+  FEMB200_ERR_CUDA = 22,        /* CUDA runtime failure; text via femb200_last_cuda_error */
+  FEMB200_ERR_TOO_LARGE = 23    /* index width exceeded (row with > 65535 node blocks, nnz/row > 2^31) */
+};
+
+/* Everything AddIsoparametric evaluates ONCE per call on the host (assembler_isoparametric.go:29-71)
+ * crosses the boundary as tables, so user-defined fem.Isoparametric elements keep working:
+ *   d     = len(elemT.BasisDiff(0)) / elemT.LenNodes()                      (:40)
+ *   nn    = elemT.LenNodes(), ndn = elemT.Dofs().Count()                    (:44-46)
+ *   Npg   [nqp][nn]     = elemT.Basis(upg[q])                               (:69)
+ *   dNpg  [nqp][d][nn]  = elemT.BasisDiff(upg[q])   row-major               (:70)
+ *   wpg   [nqp]         = quadrature weights                                (:56)
+ *   C     [dimC][dimC]  = c.Constitutive() copied dense, row-major          (:29,:63)
+ *   dofmap[ndn]         = mapdofs(modelDofs, elemT.Dofs())                  (fem.go:155-172)
+ * model_dofs_per_node = modelDofs.Count(); the reference requires it to equal ndn
+ * (fem.go:138 + assembler.go:148-150 panic "bad length"), the shim checks that before calling. */
+typedef struct femb200_elem_desc {
+  int32_t d, nn, ndn, nqp, dimC, bkind;
+  int32_t model_dofs_per_node;
+  int32_t reserved;
+  const double *Npg;
+  const double *dNpg;
+  const double *wpg;
+  const double *C;
+  const int32_t *dofmap;
+} femb200_elem_desc;
+
+typedef struct femb200_ctx femb200_ctx;             /* one CUDA device + stream + memory pool */
+typedef struct femb200_assembler femb200_assembler; /* twin of fem.GeneralAssembler (assembler.go:13-18) */
+
+int femb200_abi_version(void);
+
+/* Context on CUDA device `device` (ordinal).  Fails with FEMB200_ERR_CUDA when there is no GPU. */
+int femb200_ctx_create(int device, femb200_ctx **out);
+void femb200_ctx_destroy(femb200_ctx *ctx);
+/* Runs on an externally owned stream (cudaStream_t as void*), e.g. torch's current stream. */
+int femb200_ctx_set_stream(femb200_ctx *ctx, void *cuda_stream);
+const char *femb200_last_cuda_error(const femb200_ctx *ctx);
+
+/* fem.NewGeneralAssembler(nodes []r3.Vec, modelDofs) (assembler.go:21-28).
+ * nodes: n_nodes x {X,Y,Z} float64, 24-byte stride (the memory of a Go []r3.Vec).
+ * nodes_on_device != 0: `nodes` is a device pointer that stays valid for the assembler's life. */
+int femb200_assembler_create(femb200_ctx *ctx, const double *nodes, int64_t n_nodes,
+                             int32_t model_dofs_per_node, int32_t nodes_on_device,
+                             femb200_assembler **out);
+void femb200_assembler_destroy(femb200_assembler *ga);
+
+/* (*GeneralAssembler).AddIsoparametric (assembler_isoparametric.go:28-123) for n_elem elements whose
+ * connectivity the shim flattened from getElement(i) (fem.go:141): conn[n_elem][nn], 32- or 64-bit
+ * (Go int), on the host or already on the device.  Symbolic phase, numeric phase and the deterministic
+ * row reduction all run on the GPU; the result is accumulated into K (repeated calls add up, :121).
+ * On an element error K is left untouched (:118-120) and the lowest failing element is reported. */
+int femb200_add_isoparametric(femb200_assembler *ga, const femb200_elem_desc *desc,
+                              const void *conn, int32_t conn_is_int64, int32_t conn_on_device,
+                              int64_t n_elem);
+
+/* After a non-zero status: which error, the lowest failing element index and its first failing
+ * quadrature point (-1 when not applicable). */
+int femb200_last_error(const femb200_assembler *ga, int32_t *kind, int64_t *elem, int32_t *qp);
+
+/* (*GeneralAssembler).TotalDofs (assembler.go:34-37) and the size of Ksolid() (assembler.go:31). */
+int64_t femb200_total_dofs(const femb200_assembler *ga);
+int64_t femb200_nnz(const femb200_assembler *ga);
+/* K as canonical CSR (rows and columns ascending, every emitted (row,col) pair kept, duplicates
+ * summed in ascending element index then call order): indptr[ndof+1] int64, indices[nnz] int32,
+ * values[nnz] float64, copied into caller memory.  NULL pointers are skipped. */
+int femb200_csr_copy(const femb200_assembler *ga, int64_t *indptr, int32_t *indices, double *values);
+/* The same arrays left on the device (valid until the next add/destroy). */
+int femb200_csr_device(const femb200_assembler *ga, const int64_t **indptr, const int32_t **indices,
+                       const double **values);
+/* lap.Sparse.At(i,j) (call sites example_test.go:38, patch_test.go:80): one entry, 0 if absent. */
+int femb200_csr_at(const femb200_assembler *ga, int64_t i, int64_t j, double *out);
+/* K*x on the device, x and y on the host (forces.MulVec(K,u), patch_test.go:92). */
+int femb200_csr_matvec(const femb200_assembler *ga, const double *x, double *y);
+
+/* Element -> CSR slot map of the last add call (north_star subsystem 1):
+ * slot[e][a][b] = index into the node-block CSR of block (node a of e, node b of e); the scalar entry
+ * of dof pair (i,j) sits at values[indptr[mdpn*node_a+dofmap[i]] + pos*nu + j'].  Copied to the host. */
+int femb200_last_slot_map(const femb200_assembler *ga, int64_t *slot /* [n_elem][nn][nn] */);
+
+/* (*GeneralAssembler).IsoparametricStrains (assembler_isoparametric.go:126-213): strains[n_elem][nqp][dimC]
+ * = B(q) * u[elemDofs], host in / host out. */
+int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc *desc,
+                                  const void *conn, int32_t conn_is_int64, int32_t conn_on_device,
+                                  int64_t n_elem, const double *u, double *strains);
+
+/* Device-side phase timers of the last add call, milliseconds (CUDA events on the context stream):
+ * [0] upload+validate [1] node->element adjacency [2] row pattern [3] CSR expand
+ * [4] numeric + row reduction [5] merge into K [6] total device [7] numeric kernel launches in total. */
+#define FEMB200_N_TIMERS 8
+int femb200_phase_ms(const femb200_assembler *ga, float out[FEMB200_N_TIMERS]);
+/* Number of kernels this library launched since the context was created (bench.py "gpu_launches"). */
+int64_t femb200_kernel_launches(const femb200_ctx *ctx);
+/* Blocks until all work queued on the context stream is done. */
+int femb200_sync(femb200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,411 @@
+"""Parity tests proper: the CUDA path (through the host mirror and the C ABI) against the CPU oracle on the
+same inputs.  Bar: CSR pattern (indptr/indices) bit-exact, values within 1e-12 normalised per SURVEY 8-Q8
+(|a-b| <= 1e-12*max(|b|, sum_e|Ke_e[i][j]|)).  Run on a B200: python -m pytest tests -m gpu."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import KINDS, compare_csr, go_rand_float64
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+EX = json.load(open(os.path.join(GOLD, "example_test_outputs.json")))
+TOL = 1e-12
+
+
+def elem_of(pkg, name, **kw):
+    return {"tetra4": pkg.elements.Tetra4, "tetra10": pkg.elements.Tetra10, "hexa8": pkg.elements.Hexa8, "hexa20": pkg.elements.Hexa20,
+            "quad4": pkg.elements.Quad4, "quad8": pkg.elements.Quad8, "triangle3": pkg.elements.Triangle3}[name](**kw)
+
+
+def constituter_of(pkg, mode, p0, p1=0.0):
+    s = pkg.solids
+    return [s.Isotropic(p0, p1).Solid3D, s.Isotropic(p0, p1).Axisymmetric, s.Isotropic(p0, p1).PlaneStess, s.Isotropic(p0, p1).PlaneStrain,
+            s.IsotropicConductivity(p0).Solid3D, s.IsotropicConductivity(p0).Plane, s.IsotropicConductivity(p0).Axisymmetric][mode]()
+
+
+def assemble_both(pkg, O, name, nodes, conn, mode, flags, p0=200e9, p1=0.3, quad_order=0, node_dofs=0):
+    ga = pkg.fem.NewGeneralAssembler(nodes, flags)
+    err = ga.AddIsoparametric(elem_of(pkg, name, QuadratureOrder=quad_order, NodeDofs=node_dofs), constituter_of(pkg, mode, p0, p1), conn.shape[0], conn)
+    assert err is None, err
+    C, bk = O.constitutive(mode, p0, p1)
+    og = O.GeneralAssembler(nodes, flags)
+    og.add_isoparametric(KINDS[name]["kind"], C, bk, conn, quad_order=quad_order, node_dofs=node_dofs)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    return ga, ga.Ksolid().csr(), (rp, ri, rv), ab
+
+
+# ---- the reference's golden examples, through the GPU ------------------------------------------------
+def _fmt_equal(name, K):
+    fmt, G = EX[name]["format"], np.array(EX[name]["K"])
+    F = np.array([[float(fmt % v) for v in row] for row in K])
+    assert np.array_equal(F, G), name
+
+
+def test_golden_examples_on_gpu(pkg):
+    fem, el, so = pkg.fem, pkg.elements, pkg.solids
+    q = [[20, 0, 0], [30, 0, 0], [30, 1, 0], [20, 1, 0]]
+    ga = fem.NewGeneralAssembler(q, el.Quad4().Dofs())
+    assert ga.AddIsoparametric(el.Quad4(), so.Isotropic(1000, 0.33).Axisymmetric(), 1, lambda i: [0, 1, 2, 3]) is None
+    _fmt_equal("ExampleGeneralAssembler_AddIsoparametric_axisymmetric", ga.Ksolid().dense())
+    ga = fem.NewGeneralAssembler([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], el.Tetra4().Dofs())
+    assert ga.AddIsoparametric(el.Tetra4(), so.Isotropic(200e9, 0.3).Solid3D(), 1, lambda i: [0, 1, 2, 3]) is None
+    _fmt_equal("ExampleGeneralAssembler", ga.Ksolid().dense())
+    ga = fem.NewGeneralAssembler([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], el.Quad4().Dofs())
+    assert ga.AddIsoparametric(el.Quad4(), so.Isotropic(1, 0.3).PlaneStess(), 1, lambda i: [0, 1, 2, 3]) is None
+    _fmt_equal("ExampleGeneralAssembler_AddIsoparametric_quad4PlaneStress", ga.Ksolid().dense())
+    et = el.Quad4(NodeDofs=fem.DofPosX)
+    ga = fem.NewGeneralAssembler(q, et.Dofs())
+    assert ga.AddIsoparametric(et, so.IsotropicConductivity(45).Axisymmetric(), 1, lambda i: [0, 1, 2, 3]) is None
+    _fmt_equal("ExampleGeneralAssembler_AddIsoparametric_axisymmetricThermal", ga.Ksolid().dense())
+
+
+# ---- every element type of the north star against the oracle ------------------------------------------
+@pytest.mark.parametrize("name,size", [("tetra4", 6), ("tetra10", 3), ("hexa8", 5), ("hexa20", 3), ("quad4", 17), ("quad8", 9), ("triangle3", 13)])
+def test_element_types_match_oracle(pkg, O, meshes, name, size):
+    nodes, conn = meshes.mesh_for(name, size)
+    k = KINDS[name]
+    ga, got, ref, ab = assemble_both(pkg, O, name, nodes, conn, k["mode"], k["flags"])
+    nerr, rel = compare_csr(got, ref, ab, TOL)
+    print(f"{name}: nelem={conn.shape[0]} nnz={got[2].size} max normalised err={nerr:.2e} max rel err={rel:.2e} phases={ga.phase_ms()}")
+
+
+@pytest.mark.parametrize("name,mode,flags", [("quad4", 2, 3), ("quad8", 3, 3), ("triangle3", 2, 3), ("quad4", 3, 3)])
+def test_plane_kinds_match_oracle(pkg, O, meshes, name, mode, flags):
+    nodes, conn = meshes.mesh_for(name, 8)
+    _, got, ref, ab = assemble_both(pkg, O, name, nodes, conn, mode, flags, 70e9, 0.25)
+    compare_csr(got, ref, ab, TOL)
+
+
+@pytest.mark.parametrize("name,mode,size", [("hexa8", 4, 4), ("tetra4", 4, 4), ("tetra10", 4, 2), ("hexa20", 4, 2), ("quad4", 5, 9),
+                                            ("quad8", 6, 6), ("triangle3", 6, 7), ("quad4", 6, 9)])
+def test_thermal_kinds_match_oracle(pkg, O, meshes, name, mode, size):
+    nodes, conn = meshes.mesh_for(name, size)
+    _, got, ref, ab = assemble_both(pkg, O, name, nodes, conn, mode, 1, 45.0, 0.0, node_dofs=1)
+    compare_csr(got, ref, ab, TOL)
+
+
+@pytest.mark.parametrize("name,order", [("hexa8", 1), ("hexa8", 3), ("hexa8", 4), ("quad4", 1), ("quad4", 5), ("quad8", 2), ("triangle3", 3), ("hexa20", 2)])
+def test_quadrature_orders(pkg, O, meshes, name, order):
+    nodes, conn = meshes.mesh_for(name, 3)
+    k = KINDS[name]
+    _, got, ref, ab = assemble_both(pkg, O, name, nodes, conn, k["mode"], k["flags"], quad_order=order)
+    compare_csr(got, ref, ab, TOL)
+
+
+def test_global_accumulator_path_matches(pkg, O, meshes, monkeypatch):
+    """Rows too long for shared memory fall back to accumulating straight into the CSR slots."""
+    monkeypatch.setenv("FEMB200_FORCE_GLOBAL_ACC", "1")
+    for name, size in (("tetra4", 4), ("hexa8", 3), ("quad4", 9)):
+        nodes, conn = meshes.mesh_for(name, size)
+        k = KINDS[name]
+        _, got, ref, ab = assemble_both(pkg, O, name, nodes, conn, k["mode"], k["flags"])
+        compare_csr(got, ref, ab, TOL)
+
+
+def test_high_valence_node_long_rows(pkg, O):
+    """A fan of 300 triangles around one hub node: the hub row has 301 blocks (spills the shared list)."""
+    n = 300
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    nodes = np.zeros((n + 1, 3))
+    nodes[1:, 0] = 5 + np.cos(ang)
+    nodes[1:, 1] = 5 + np.sin(ang)
+    nodes[0, :2] = 5
+    conn = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)], dtype=np.int64)
+    _, got, ref, ab = assemble_both(pkg, O, "triangle3", nodes, conn, 1, 3, 1e5, 0.3)
+    compare_csr(got, ref, ab, TOL)
+    assert np.diff(got[0]).max() == 2 * (n + 1)
+
+
+def test_fixture_meshes(pkg, O):
+    m = json.load(open(os.path.join(GOLD, "ruc_hexa8.json")))
+    nodes, h8 = np.array(m["nodes"]), np.array(m["hexa8"], dtype=np.int64)
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    err = ga.AddIsoparametric(pkg.elements.Hexa8(), pkg.solids.Isotropic(4.8e3, 0.34).Solid3D(), len(h8), h8)
+    assert err is not None and err.msg == "negative determinant of jacobian of element #0, Check node ordering"
+    assert ga.Ksolid().NonZero() == 0                       # K untouched (assembler_isoparametric.go:118-121)
+    fixed = h8[:, [4, 5, 6, 7, 0, 1, 2, 3]]
+    _, got, ref, ab = assemble_both(pkg, O, "hexa8", nodes, fixed, 0, 7, 4.8e3, 0.34)
+    compare_csr(got, ref, ab, TOL)
+    m = json.load(open(os.path.join(GOLD, "bimetallic_quad8.json")))
+    nodes, q8 = np.array(m["nodes"]), np.array(m["quad8"], dtype=np.int64)
+    _, got, ref, ab = assemble_both(pkg, O, "quad8", nodes, q8, 3, 3, 200e3, 0.3)
+    compare_csr(got, ref, ab, TOL)
+    shifted = nodes.copy()
+    shifted[:, 0] += 200
+    _, got, ref, ab = assemble_both(pkg, O, "quad8", shifted, q8, 1, 3, 200e3, 0.3)
+    compare_csr(got, ref, ab, TOL)
+
+
+# ---- error behaviour -------------------------------------------------------------------------------
+def test_errors_report_lowest_element_and_leave_k_untouched(pkg, O, meshes):
+    nodes, conn = meshes.bcc_tetra4(4)
+    bad = conn.copy()
+    for e in (500, 37, 212):                                # swapping two vertices flips the Jacobian sign
+        bad[e, [2, 3]] = bad[e, [3, 2]]
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    c = pkg.solids.Isotropic(200e9, 0.3).Solid3D()
+    assert ga.AddIsoparametric(pkg.elements.Tetra4(), c, len(conn) // 2, conn[: len(conn) // 2]) is None
+    before = ga.Ksolid().csr()
+    err = ga.AddIsoparametric(pkg.elements.Tetra4(), c, len(bad), bad)
+    assert err.msg == "negative determinant of jacobian of element #37, Check node ordering"
+    after = ga.Ksolid().csr()
+    assert all(np.array_equal(a, b) for a, b in zip(before, after))
+    og = O.GeneralAssembler(nodes, 7)
+    Cm, bk = O.constitutive(0, 200e9, 0.3)
+    with pytest.raises(O.OracleError) as ei:
+        og.add_isoparametric(O.TETRA4, Cm, bk, bad)
+    assert (ei.value.kind, ei.value.elem) == (1, 37)
+    # degenerate element -> "zero determinant" (dJac < 1e-12 absolute)
+    flat = conn.copy()
+    flat[11, 3] = flat[11, 2]
+    err = ga.AddIsoparametric(pkg.elements.Tetra4(), c, len(flat), flat)
+    assert err.msg == "zero determinant of jacobian of element #11, Check element shape for bad aspect ratio"
+    # tiny but valid elements trip the ABSOLUTE 1e-12 threshold too (8-Q3)
+    tiny = pkg.fem.NewGeneralAssembler(nodes * 1e-5, 7)
+    err = tiny.AddIsoparametric(pkg.elements.Tetra4(), c, len(conn), conn)
+    assert err is not None and err.msg.startswith("zero determinant of jacobian of element #0")
+    # node index out of range -> the reference panics on the slice bound
+    oob = conn.copy()
+    oob[77, 1] = nodes.shape[0]
+    err = ga.AddIsoparametric(pkg.elements.Tetra4(), c, len(oob), oob)
+    assert err is not None and err.is_panic and "#77" in err.msg
+    # axisymmetric element on the axis: r = 0 -> 1/r = Inf, scale stays finite (0) => no NaN-scale error,
+    # but NaN coordinates give a NaN radius -> ":106 NaN scale value"
+    qn, qc = meshes.quad4_grid(3, 3)
+    qn[5, 0] = np.nan
+    g2 = pkg.fem.NewGeneralAssembler(qn, 3)
+    err = g2.AddIsoparametric(pkg.elements.Quad4(), pkg.solids.Isotropic(1e3, 0.3).Axisymmetric(), len(qc), qc)
+    og2 = O.GeneralAssembler(qn, 3)
+    Ca, bka = O.constitutive(1, 1e3, 0.3)
+    with pytest.raises(O.OracleError) as ei:
+        og2.add_isoparametric(O.QUAD4, Ca, bka, qc)
+    assert err is not None
+    if ei.value.kind == 4:
+        assert err.msg == f"NaN scale value returned by SetStrainDisplacementMatrix at element #{ei.value.elem}, quad {ei.value.qp}"
+
+
+def test_host_side_errors(pkg, meshes):
+    nodes, conn = meshes.bcc_tetra4(2)
+    fem, el, so = pkg.fem, pkg.elements, pkg.solids
+    c = so.Isotropic(200e9, 0.3).Solid3D()
+    ga = fem.NewGeneralAssembler(nodes, 7)
+    err = ga.AddIsoparametric(el.Tetra4(), c, 3, lambda i: [0, 1, 2, 3] if i != 1 else [0, 1, 2])
+    assert err.msg == "element #1 of 3 nodes expected to be of 4 nodes"                       # fem.go:143
+    err = ga.AddIsoparametric(el.Tetra4(), c, len(conn), conn, orientation=[1, 0, 0])
+    assert err.msg == "arbitrary constitutive orientation not implemented yet"                # :87
+    err = fem.NewGeneralAssembler(nodes, fem.DofPosX | fem.DofPosY).AddIsoparametric(el.Tetra4(), c, len(conn), conn)
+    assert err.msg == "model dofs 12 does not contain all element dofs 123"                   # fem.go:158
+    err = fem.NewGeneralAssembler(nodes, fem.Dof6).AddIsoparametric(el.Tetra4(), c, len(conn), conn)
+    assert err.is_panic and err.msg == "bad length"                                           # assembler.go:149
+    err = ga.AddIsoparametric(el.Hexa8(QuadratureOrder=7), c, 0, np.zeros((0, 8)))
+    assert err.msg == "bad quadrature result from isoparametric element"
+    err = fem.NewGeneralAssembler(nodes, 3).AddIsoparametric(el.Triangle6(), so.Isotropic(1, 0.3).PlaneStess(), 0, np.zeros((0, 6)))
+    assert err.is_panic                                                                        # 8-Q5
+    err = ga.AddIsoparametric(el.Tetra4(), so.Isotropic(1.0, 0.5).Solid3D(), len(conn), conn)
+    assert "condition number" in err.msg                                                       # isotropic.go:24-26
+    assert ga.Ksolid().NonZero() == 0
+
+
+# ---- assembler semantics ---------------------------------------------------------------------------
+def test_repeated_calls_accumulate_and_mix_element_types(pkg, O, meshes):
+    nodes, conn = meshes.hexa8_grid(4, 4, 4)
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    og = O.GeneralAssembler(nodes, 7)
+    Cm, bk = O.constitutive(0, 200e9, 0.3)
+    h = conn.shape[0] // 3
+    c1, c2 = pkg.solids.Isotropic(200e9, 0.3).Solid3D(), pkg.solids.Isotropic(70e9, 0.33).Solid3D()
+    C2, _ = O.constitutive(0, 70e9, 0.33)
+    assert ga.AddIsoparametric(pkg.elements.Hexa8(), c1, h, conn[:h]) is None
+    og.add_isoparametric(O.HEXA8, Cm, bk, conn[:h])
+    assert ga.AddIsoparametric(pkg.elements.Hexa8(), c2, conn.shape[0] - h, conn[h:]) is None
+    og.add_isoparametric(O.HEXA8, C2, bk, conn[h:])
+    # a third call with a different element type on the same nodes (tets over the first cells)
+    tets = np.array([[conn[e, 0], conn[e, 1], conn[e, 3], conn[e, 4]] for e in range(10)], dtype=np.int64)
+    assert ga.AddIsoparametric(pkg.elements.Tetra4(), c1, len(tets), tets) is None
+    og.add_isoparametric(O.TETRA4, Cm, bk, tets)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    compare_csr(ga.Ksolid().csr(), (rp, ri, rv), ab, TOL)
+
+
+def test_deterministic_bitwise(pkg, meshes):
+    nodes, conn = meshes.bcc_tetra4(8)
+    c = pkg.solids.Isotropic(200e9, 0.3).Solid3D()
+    runs = []
+    for _ in range(3):
+        ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+        assert ga.AddIsoparametric(pkg.elements.Tetra4(), c, conn.shape[0], conn) is None
+        runs.append(ga.Ksolid().csr())
+    for r in runs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(runs[0], r))       # bit-identical values
+
+
+def test_empty_and_degenerate_inputs(pkg):
+    fem, el, so = pkg.fem, pkg.elements, pkg.solids
+    nodes = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0], [9, 9, 9]])
+    ga = fem.NewGeneralAssembler(nodes, 7)
+    assert ga.TotalDofs() == 15
+    assert ga.AddIsoparametric(el.Tetra4(), so.Isotropic(1, 0.3).Solid3D(), 0, np.zeros((0, 4))) is None
+    ip, ix, v = ga.Ksolid().csr()
+    assert ip.tolist() == [0] * 16 and ix.size == 0
+    assert ga.AddIsoparametric(el.Tetra4(), so.Isotropic(1, 0.3).Solid3D(), 1, lambda i: [0, 1, 2, 3]) is None
+    ip, ix, v = ga.Ksolid().csr()
+    assert ip[12] == 144 and ip[15] == 144          # node 4 unreferenced -> three empty rows
+    K = ga.Ksolid()
+    assert K.At(0, 0) == v[0] and K.At(14, 14) == 0.0 and K.Dims() == (15, 15)
+    assert fem.NewGeneralAssembler(np.zeros((0, 3)), 7).TotalDofs() == 0
+
+
+def test_noncontiguous_model_dofs_quirk(pkg, O, meshes):
+    """fem.go:155-172 maps DofPosX|DofPosZ to dofmap [0,0]: both element dofs land on the same global dof.
+    The drop-in reproduces it (rows of the second dof stay empty)."""
+    nodes, conn = meshes.quad4_grid(4, 4)
+    flags = pkg.fem.DofPosX | pkg.fem.DofPosZ
+    ga = pkg.fem.NewGeneralAssembler(nodes, flags)
+    et = pkg.elements.Quad4(NodeDofs=flags)
+    assert ga.AddIsoparametric(et, pkg.solids.Isotropic(1e3, 0.3).PlaneStess(), len(conn), conn) is None
+    og = O.GeneralAssembler(nodes, flags)
+    Cm, bk = O.constitutive(2, 1e3, 0.3)
+    og.add_isoparametric(O.QUAD4, Cm, bk, conn, node_dofs=flags)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    compare_csr(ga.Ksolid().csr(), (rp, ri, rv), ab, TOL)
+    assert np.all(np.diff(rp)[1::2] == 0)
+
+
+def test_slot_map(pkg, meshes):
+    nodes, conn = meshes.hexa8_grid(3, 3, 3)
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    assert ga.AddIsoparametric(pkg.elements.Hexa8(), pkg.solids.Isotropic(1e3, 0.3).Solid3D(), len(conn), conn) is None
+    indptr, indices, _ = ga.Ksolid().csr()
+    slot = ga.slot_map(len(conn), 8)
+    blkptr = indptr[::3] // 9
+    for e in (0, 13, 26):
+        for a in range(8):
+            for b in range(8):
+                s = slot[e, a, b]
+                row = conn[e, a]
+                assert blkptr[row] <= s < blkptr[row + 1]
+                pos = s - blkptr[row]
+                assert indices[indptr[3 * row] + 3 * pos] == 3 * conn[e, b]
+
+
+def test_matvec_and_rigid_body_modes(pkg, meshes):
+    nodes, conn = meshes.bcc_tetra4(6)
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    assert ga.AddIsoparametric(pkg.elements.Tetra4(), pkg.solids.Isotropic(200e9, 0.3).Solid3D(), len(conn), conn) is None
+    K = ga.Ksolid()
+    ip, ix, v = K.csr()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((v, ix, ip), shape=K.Dims())
+    x = np.random.default_rng(0).standard_normal(A.shape[0])
+    assert np.allclose(K.MulVec(x), A @ x, rtol=1e-12, atol=1e-12 * np.abs(v).max())
+    for ax in range(3):
+        u = np.zeros(A.shape[0])
+        u[ax::3] = 1
+        assert np.abs(K.MulVec(u)).max() <= 1e-9 * np.abs(v).max()
+
+
+# ---- patch tests of the reference through the GPU -----------------------------------------------------
+def _washer():
+    ri, lx, ly = 1, 0.24, 0.12
+    r = go_rand_float64(8)
+    nodes = [[ri, 0, 0], [ri + lx, 0, 0], [ri + lx, ly, 0], [ri, ly, 0],
+             [ri + lx / 3 + (r[0] - 0.5) * lx / 4, ly / 3 + (r[1] - 0.5) * ly / 4, 0],
+             [ri + lx * 2 / 3 - (r[2] - 0.5) * lx / 4, ly / 3 + (r[3] - 0.5) * ly / 4, 0],
+             [ri + lx * 2 / 3 - (r[4] - 0.5) * lx / 4, ly * 2 / 3 - (r[5] - 0.5) * ly / 4, 0],
+             [ri + lx / 3 + (r[6] - 0.5) * lx / 4, ly * 2 / 3 - (r[7] - 0.5) * ly / 4, 0]]
+    elems = [[0, 1, 5, 4], [1, 2, 6, 5], [6, 2, 3, 7], [0, 4, 7, 3], [4, 5, 6, 7]]
+    return np.array(nodes), np.array(elems, dtype=np.int64), ri, lx, ly
+
+
+def test_axisymmetric_patch_test_on_gpu(pkg, O):            # patch_test.go:19-157
+    nodes, elems, ri, lx, ly = _washer()
+    fem = pkg.fem
+    mat = pkg.solids.Isotropic(1e6, 0.25).Axisymmetric()
+    et = pkg.elements.Quad4()
+    ga = fem.NewGeneralAssembler(nodes, et.Dofs())
+    assert ga.AddIsoparametric(et, mat, len(elems), lambda i: elems[i]) is None
+    K = ga.Ksolid().dense()
+    fix = fem.NewFixity(fem.DofPosX | fem.DofPosY, len(nodes))
+    u = np.zeros(16)
+    for i, n in enumerate(nodes):
+        if n[1] == ly or n[1] == 0 or n[0] == ri or n[0] == ri + lx:
+            u[2 * i], u[2 * i + 1] = n[0] / 1000, (n[1] + n[0]) / 1000
+            fix.Fix(i, fem.DofPosX | fem.DofPosY)
+    free, fixed = fix.FreeDofs(), fix.FixedDofs()
+    u[free] = np.linalg.solve(K[np.ix_(free, free)], -K[np.ix_(free, fixed)] @ u[fixed])
+    s = ga.IsoparametricStrains(u, et, mat, elems)
+    assert np.all(np.abs(s - 1e-3) / 1e-3 <= 3e-2)
+    Cm, bk = O.constitutive(1, 1e6, 0.25)
+    og = O.GeneralAssembler(nodes, 3)
+    og.add_isoparametric(O.QUAD4, Cm, bk, elems)
+    assert np.allclose(s, og.strains(u, O.QUAD4, Cm, bk, elems), rtol=1e-11, atol=1e-15)
+
+
+def test_thermal_patch_test_on_gpu(pkg):                    # patch_test.go:162-247
+    nodes, elems, ri, lx, ly = _washer()
+    fem = pkg.fem
+    et = pkg.elements.Quad4(NodeDofs=1)
+    ga = fem.NewGeneralAssembler(nodes, 1)
+    assert ga.AddIsoparametric(et, pkg.solids.IsotropicConductivity(1.0).Axisymmetric(), len(elems), lambda i: elems[i]) is None
+    K = ga.Ksolid().dense()
+    fix = fem.NewFixity(fem.DofPosX, len(nodes))
+    T = np.zeros(8)
+    for i, n in enumerate(nodes):
+        if n[1] == ly:
+            T[i] = 100
+            fix.Fix(i, 1)
+        elif n[1] == 0:
+            fix.Fix(i, 1)
+    free, fixed = fix.FreeDofs(), fix.FixedDofs()
+    T[free] = np.linalg.solve(K[np.ix_(free, free)], -K[np.ix_(free, fixed)] @ T[fixed])
+    exp = 100 * nodes[:, 1] / ly
+    assert np.all(np.abs(T - exp) / (exp + 1e-2) <= 1e-2)
+
+
+@pytest.mark.parametrize("name,size,mode,flags", [("hexa8", 4, 0, 7), ("tetra10", 2, 0, 7), ("quad8", 5, 3, 3), ("triangle3", 6, 1, 3)])
+def test_strains_match_oracle(pkg, O, meshes, name, size, mode, flags):
+    nodes, conn = meshes.mesh_for(name, size)
+    ga = pkg.fem.NewGeneralAssembler(nodes, flags)
+    u = np.random.default_rng(3).standard_normal(ga.TotalDofs()) * 1e-3
+    s = ga.IsoparametricStrains(u, elem_of(pkg, name), constituter_of(pkg, mode, 1e5, 0.3), conn)
+    Cm, bk = O.constitutive(mode, 1e5, 0.3)
+    og = O.GeneralAssembler(nodes, flags)
+    ref = og.strains(u, KINDS[name]["kind"], Cm, bk, conn)
+    assert s.shape == ref.shape
+    assert np.allclose(s, ref, rtol=1e-11, atol=1e-13 * np.abs(ref).max())
+
+
+# ---- BASELINE config 1 at full size: size-independent properties ----------------------------------------
+def test_config1_full_size_properties(pkg, O, meshes):
+    """Tetra4 BCC N=48: 1,299,456 elements / 684,723 dofs (benchmark_test.go largest case).  The oracle is
+    run on the same mesh too (tens of seconds): pattern bit-exact and values to 1e-12."""
+    N = 48
+    nodes, conn = meshes.bcc_tetra4(N)
+    assert (nodes.shape[0] * 3, conn.shape[0]) == (684723, 1299456)
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    assert ga.AddIsoparametricFlat(pkg.elements.Tetra4(), pkg.solids.Isotropic(200e9, 0.3).Solid3D(), conn) is None
+    ip, ix, v = ga.Ksolid().csr()
+    nblk = 30 * N ** 3 + 9 * N ** 2 - 15 * N - 23
+    assert v.size == 9 * nblk == 30039777
+    assert int((np.diff(ip) == 0).sum()) == 24
+    assert np.all(np.diff(ix.astype(np.int64))[np.setdiff1d(np.arange(ix.size - 1), ip[1:-1] - 1)] > 0)   # ascending in rows
+    import scipy.sparse as sp
+    A = sp.csr_matrix((v, ix, ip), shape=(684723, 684723))
+    scale = np.abs(v).max()
+    assert abs(A - A.T).max() <= 1e-12 * scale                             # symmetry
+    for ax in range(3):                                                     # rigid translations
+        u = np.zeros(684723)
+        u[ax::3] = 1
+        assert np.abs(A @ u).max() <= 1e-9 * scale
+    d = A.diagonal()
+    assert np.all(d[np.diff(ip) > 0] > 0)
+    print("config1 phases (ms):", ga.phase_ms())
+    Cm, bk = O.constitutive(0, 200e9, 0.3)
+    og = O.GeneralAssembler(nodes, 7)
+    og.add_isoparametric(O.TETRA4, Cm, bk, conn)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    nerr, rel = compare_csr((ip, ix, v), (rp, ri, rv), ab, TOL)
+    print(f"config1 vs oracle: max normalised err {nerr:.2e}, max rel err {rel:.2e}, oracle {og.last_seconds():.1f}s")
