@@ -70,26 +70,69 @@ template <bool TAB_CONST> struct Tab {
   template <int D, int NN> __device__ __forceinline__ double dN(int q, int i, int b) const { return at(offDN + (q * D + i) * NN + b); }
 };
 
-// ---- d x d inverse / determinant (closed form; the reference uses LU, differences are O(eps)) -----
+// ---- d x d determinant and inverse --------------------------------------------------------------
+// The determinant follows the reference's algorithm class: LU with partial pivoting (gonum mat.Det ->
+// Dgetf2, first-max pivot, multipliers = a * (1/pivot)), det = sign * prod(u_ii), so that exactly singular
+// Jacobians (collapsed elements: two identical rows) give EXACTLY 0 -> "zero determinant", and the
+// sign of a degenerate element is not decided by FMA rounding noise.  The inverse is the adjugate
+// scaled by 1/det (differences to the reference's LU solve are O(eps * cond)).
+template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D][D]) {
+  double A[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) A[i][j] = Jin[i][j];
+  double det = 1.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    // first index of the largest |A[i][j]|, i >= j; swap it into row j (predicated, static indices)
+    double best = fabs(A[j][j]);
+    int p = j;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      const double v = fabs(A[i][j]);
+      if (v > best) { best = v; p = i; }
+    }
+#pragma unroll
+    for (int i = j + 1; i < D; ++i)
+      if (p == i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) { const double t = A[j][k]; A[j][k] = A[i][k]; A[i][k] = t; }
+        det = -det;
+      }
+    const double piv = A[j][j];
+    det = __dmul_rn(det, piv);
+    if (piv != 0.0) {
+      const double r = 1.0 / piv;
+#pragma unroll
+      for (int i = j + 1; i < D; ++i) {
+        const double l = __dmul_rn(A[i][j], r);
+#pragma unroll
+        for (int k = j + 1; k < D; ++k) A[i][k] = __dsub_rn(A[i][k], __dmul_rn(l, A[j][k])); // no FMA: same rounding as the reference's LU
+      }
+    }
+  }
+  return det;
+}
+
 template <int D> __device__ __forceinline__ double inv_det(const double (&J)[D][D], double (&inv)[D][D]);
 template <> __device__ __forceinline__ double inv_det<1>(const double (&J)[1][1], double (&inv)[1][1]) {
   inv[0][0] = 1.0 / J[0][0];
   return J[0][0];
 }
 template <> __device__ __forceinline__ double inv_det<2>(const double (&J)[2][2], double (&inv)[2][2]) {
-  const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  const double det = lu_det<2>(J);
   const double r = 1.0 / det;
   inv[0][0] = J[1][1] * r; inv[0][1] = -J[0][1] * r;
   inv[1][0] = -J[1][0] * r; inv[1][1] = J[0][0] * r;
   return det;
 }
 template <> __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&inv)[3][3]) {
-  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
-  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  const double det = lu_det<3>(J);
   const double r = 1.0 / det;
-  inv[0][0] = c00 * r; inv[1][0] = c01 * r; inv[2][0] = c02 * r;
+  inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * r;
+  inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * r;
+  inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * r;
   inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
   inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
   inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
@@ -126,7 +169,7 @@ __device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double 
     for (int i = 0; i < D; ++i) {
       const double dn = tab.template dN<D, NN>(q, i, b);
 #pragma unroll
-      for (int j = 0; j < D; ++j) J[i][j] = fma(dn, X[b][j], J[i][j]);
+      for (int j = 0; j < D; ++j) J[i][j] = __dadd_rn(J[i][j], __dmul_rn(dn, X[b][j])); // jac.Mul(dN, X): node-ascending, unfused (:93)
     }
   detJ = inv_det<D>(J, inv);
   if (detJ < 0) return FEMB200_ERR_NEG_DET;

@@ -79,8 +79,12 @@ int femo_add_isoparametric(femo_assembler *ga, int kind, int quad_order, int nod
                            const int64_t *conn, int64_t nelem, int64_t *err_elem, int *err_qp);
 int64_t femo_nnz(const femo_assembler *ga);
 void femo_csr(const femo_assembler *ga, int64_t *indptr, int32_t *indices, double *values);
-/* per-entry sum of |contribution| (the normaliser s_ij of SURVEY 8-Q8), same layout as values */
+/* per-entry normaliser s_ij, same layout as values: the sum over elements and quadrature
+ * points of |dJac*w*scale| * (|B|^T |C| |B|)_ij, i.e. the sum of the absolute values of every product that
+ * enters K_ij.  Rounding-level differences between two correct implementations are bounded by a small
+ * multiple of eps * s_ij; entries that cancel (inside Ke or across elements) have |K_ij| << s_ij. */
 void femo_csr_absum(const femo_assembler *ga, double *absum);
+void femo_set_normaliser(int on); /* 0: skip the test-only normaliser (timed cpu_baseline runs) */
 
 /* element stiffness matrices only: Ke[nelem][nd][nd] (assembler_isoparametric.go:89-113) */
 int femo_element_matrices(const double *nodes3, int64_t n_nodes, int kind, int quad_order, int node_dofs,

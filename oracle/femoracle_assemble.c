@@ -286,10 +286,61 @@ static int qp_geometry(const tables *t, int q, const double *X, double *B, doubl
   return 0;
 }
 
+/* test-only: |B| for the normaliser, from |J^-1| |dN| and |N| |1/r| */
+static void abs_B(const tables *t, int q, const double *X, double *Ba) {
+  int d = t->d, nn = t->nn, nd = t->nd;
+  double jac[9], inv[9], eye[9], ga[MAXD * MAXNN];
+  const double *dN = t->dN[q];
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++) {
+      double s = 0;
+      for (int a = 0; a < nn; a++) s += dN[i * nn + a] * X[a * d + j];
+      jac[i * d + j] = s;
+      eye[i * d + j] = (i == j);
+    }
+  solve_gonum(d, jac, d, eye, inv);
+  for (int i = 0; i < d; i++)
+    for (int b = 0; b < nn; b++) {
+      double s = 0;
+      for (int j = 0; j < d; j++) s += fabs(inv[i * d + j]) * fabs(dN[j * nn + b]);
+      ga[i * nn + b] = s;
+    }
+  double radius = 0;
+  for (int i = 0; i < nn; i++) radius += X[i * d] * t->N[q][i];
+  double ri = fabs(1 / radius);
+  memset(Ba, 0, sizeof(double) * t->dimC * nd);
+  for (int i = 0; i < nn; i++) {
+    double Na = fabs(t->N[q][i]);
+    switch (t->bkind) {
+    case FEMO_B_XYZ:
+      Ba[0 * nd + i * 3] = ga[i]; Ba[1 * nd + i * 3 + 1] = ga[nn + i]; Ba[2 * nd + i * 3 + 2] = ga[2 * nn + i];
+      Ba[3 * nd + i * 3] = ga[nn + i]; Ba[3 * nd + i * 3 + 1] = ga[i];
+      Ba[4 * nd + i * 3 + 1] = ga[2 * nn + i]; Ba[4 * nd + i * 3 + 2] = ga[nn + i];
+      Ba[5 * nd + i * 3] = ga[2 * nn + i]; Ba[5 * nd + i * 3 + 2] = ga[i];
+      break;
+    case FEMO_B_PLANE:
+      Ba[0 * nd + i * 2] = ga[i]; Ba[1 * nd + i * 2 + 1] = ga[nn + i]; Ba[2 * nd + i * 2] = ga[nn + i]; Ba[2 * nd + i * 2 + 1] = ga[i];
+      break;
+    case FEMO_B_AXISYM:
+      Ba[0 * nd + i * 2] = ga[i]; Ba[1 * nd + i * 2] = Na * ri; Ba[2 * nd + i * 2 + 1] = ga[nn + i];
+      Ba[3 * nd + i * 2] = ga[nn + i]; Ba[3 * nd + i * 2 + 1] = ga[i];
+      break;
+    case FEMO_B_THERMAL:
+      for (int r = 0; r < d; r++) Ba[r * nd + i] = ga[r * nn + i];
+      break;
+    case FEMO_B_THERMAL_AXISYM:
+      Ba[0 * nd + i] = Na * ri + ga[i]; Ba[1 * nd + i] = ga[nn + i];
+      break;
+    }
+  }
+}
+
 /* Ke of one element: assembler_isoparametric.go:89-113 */
-static int element_ke(const tables *t, const double *X, double *B, double *aux1, double *aux2, double *Ke, int *err_qp) {
+static int element_ke(const tables *t, const double *X, double *B, double *aux1, double *aux2, double *Ke, int *err_qp,
+                      double *KeAbs) {
   int nd = t->nd, dimC = t->dimC;
   memset(Ke, 0, sizeof(double) * nd * nd);                   /* Ke.Zero() :89 */
+  if (KeAbs) memset(KeAbs, 0, sizeof(double) * nd * nd);
   for (int q = 0; q < t->nqp; q++) {
     double dJac, scale;
     int e = qp_geometry(t, q, X, B, &dJac, &scale);
@@ -311,6 +362,19 @@ static int element_ke(const tables *t, const double *X, double *B, double *aux1,
     double f = dJac * t->w[q] * scale;                        /* :111 left-to-right */
     for (int k = 0; k < nd * nd; k++) aux2[k] = f * aux2[k];
     for (int k = 0; k < nd * nd; k++) Ke[k] = Ke[k] + aux2[k]; /* :112 */
+    if (KeAbs) {
+      /* test-only normaliser (not in the reference): sum of |terms| of the same products,
+       * KeAbs += |f| * |B|^T |C| |B| with |B| built from |J^-1| |dN| (so cancellation inside
+       * dNxy = J^-1 dN is covered too) -- the scale against which rounding differences are graded */
+      double Ba[MAXDIMC * MAXND];
+      abs_B(t, q, X, Ba);
+      for (int i = 0; i < nd; i++)
+        for (int l = 0; l < dimC; l++) {
+          double a1 = 0;
+          for (int m = 0; m < dimC; m++) a1 += Ba[m * nd + i] * fabs(t->C[m * dimC + l]);
+          if (a1 != 0) for (int j = 0; j < nd; j++) KeAbs[i * nd + j] += fabs(f) * a1 * Ba[l * nd + j];
+        }
+    }
   }
   return 0;
 }
@@ -321,6 +385,8 @@ static void store_elem_node(double *dst, const double *nodes3, const int64_t *el
 }
 
 /* ------------------------------------------------------------------ assembler + canonical CSR */
+static int g_track_normaliser = 1;   /* tests: on; bench cpu_baseline: off (the reference computes no such thing) */
+void femo_set_normaliser(int on) { g_track_normaliser = on; }
 struct femo_assembler {
   const double *nodes; double *nodes_own;
   int64_t n_nodes; int model_flags; int64_t ndof;
@@ -351,7 +417,7 @@ void femo_csr(const femo_assembler *ga, int64_t *indptr, int32_t *indices, doubl
 }
 void femo_csr_absum(const femo_assembler *ga, double *absum) { if (ga->nnz) memcpy(absum, ga->absum, sizeof(double) * ga->nnz); }
 
-typedef struct { int32_t col; int32_t seq_hi; double v; } rowent; /* seq kept implicitly by stable order */
+typedef struct { int32_t col; int32_t seq_hi; double v; double va; } rowent; /* seq kept implicitly by stable order */
 
 static int cmp_col_stable(const void *a, const void *b) {
   const rowent *x = (const rowent *)a, *y = (const rowent *)b;
@@ -361,7 +427,7 @@ static int cmp_col_stable(const void *a, const void *b) {
 
 /* lap.Sparse.Accumulate stand-in: sum the triplets (I,J,V), in emission order per (row,col), into the
  * canonical CSR, on top of the existing content (assembler_isoparametric.go:121). */
-static void accumulate(femo_assembler *ga, const int64_t *I, const int64_t *J, const double *V, int64_t n) {
+static void accumulate(femo_assembler *ga, const int64_t *I, const int64_t *J, const double *V, const double *Vabs, int64_t n) {
   int64_t ndof = ga->ndof;
   int64_t *cnt = (int64_t *)calloc(ndof + 1, sizeof(int64_t));
   for (int64_t k = 0; k < n; k++) cnt[I[k] + 1]++;
@@ -370,7 +436,8 @@ static void accumulate(femo_assembler *ga, const int64_t *I, const int64_t *J, c
   memcpy(fill, cnt, sizeof(int64_t) * (ndof + 1));
   int32_t *bc = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
   double *bv = (double *)malloc(sizeof(double) * (n ? n : 1));
-  for (int64_t k = 0; k < n; k++) { int64_t p = fill[I[k]]++; bc[p] = (int32_t)J[k]; bv[p] = V[k]; } /* stable by row */
+  double *ba = (double *)malloc(sizeof(double) * (n ? n : 1));
+  for (int64_t k = 0; k < n; k++) { int64_t p = fill[I[k]]++; bc[p] = (int32_t)J[k]; bv[p] = V[k]; ba[p] = Vabs ? Vabs[k] : 0.0; } /* stable by row */
   free(fill);
   /* per row: stable sort by column, reduce duplicates in order, merge with the old row */
   int64_t maxrow = 0;
@@ -384,7 +451,7 @@ static void accumulate(femo_assembler *ga, const int64_t *I, const int64_t *J, c
   int64_t out = 0;
   for (int64_t r = 0; r < ndof; r++) {
     int64_t m = cnt[r + 1] - cnt[r];
-    for (int64_t k = 0; k < m; k++) { buf[k].col = bc[cnt[r] + k]; buf[k].seq_hi = (int32_t)k; buf[k].v = bv[cnt[r] + k]; }
+    for (int64_t k = 0; k < m; k++) { buf[k].col = bc[cnt[r] + k]; buf[k].seq_hi = (int32_t)k; buf[k].v = bv[cnt[r] + k]; buf[k].va = ba[cnt[r] + k]; }
     if (m > 1) qsort(buf, (size_t)m, sizeof(rowent), cmp_col_stable);
     int64_t o = ga->indptr[r], oe = ga->indptr[r + 1], k = 0;
     nptr[r] = out;
@@ -392,14 +459,14 @@ static void accumulate(femo_assembler *ga, const int64_t *I, const int64_t *J, c
       int32_t c;
       if (k >= m) c = ga->indices[o]; else if (o >= oe) c = buf[k].col; else c = ga->indices[o] < buf[k].col ? ga->indices[o] : buf[k].col;
       double s = 0, sa = 0; int have_new = 0;
-      while (k < m && buf[k].col == c) { s = have_new ? s + buf[k].v : buf[k].v; sa += fabs(buf[k].v); have_new = 1; k++; }
+      while (k < m && buf[k].col == c) { s = have_new ? s + buf[k].v : buf[k].v; sa += buf[k].va; have_new = 1; k++; }
       double val = s, ab = sa;
       if (o < oe && ga->indices[o] == c) { val = have_new ? ga->values[o] + s : ga->values[o]; ab = ga->absum[o] + sa; o++; }
       nidx[out] = c; nval[out] = val; nabs[out] = ab; out++;
     }
   }
   nptr[ndof] = out;
-  free(buf); free(bc); free(bv); free(cnt);
+  free(buf); free(bc); free(bv); free(ba); free(cnt);
   free(ga->indptr); free(ga->indices); free(ga->values); free(ga->absum);
   ga->indptr = nptr; ga->indices = nidx; ga->values = nval; ga->absum = nabs; ga->nnz = out;
 }
@@ -421,6 +488,9 @@ int femo_add_isoparametric(femo_assembler *ga, int kind, int quad_order, int nod
   int64_t *I = (int64_t *)malloc(sizeof(int64_t) * (total ? total : 1));
   int64_t *J = (int64_t *)malloc(sizeof(int64_t) * (total ? total : 1));
   double *V = (double *)malloc(sizeof(double) * (total ? total : 1));
+  const int track = g_track_normaliser;
+  double *Vabs = (double *)malloc(sizeof(double) * (track && total ? total : 1));
+  double *KeAbs = track ? (double *)malloc(sizeof(double) * nd * nd) : 0;
   double X[MAXNN * MAXD], B[MAXDIMC * MAXND], *aux1 = (double *)malloc(sizeof(double) * nd * MAXDIMC),
          *aux2 = (double *)malloc(sizeof(double) * nd * nd), *Ke = (double *)malloc(sizeof(double) * nd * nd);
   int64_t dofs[MAXND];
@@ -433,14 +503,14 @@ int femo_add_isoparametric(femo_assembler *ga, int kind, int quad_order, int nod
     for (int a = 0; a < nn; a++)                                /* storeElemDofs assembler.go:147-158 */
       for (int k = 0; k < ndn; k++) dofs[a * ndn + k] = (int64_t)t->model_dofs_per_node * elem[a] + t->dofmap[k];
     int q = -1;
-    rc = element_ke(t, X, B, aux1, aux2, Ke, &q);
+    rc = element_ke(t, X, B, aux1, aux2, Ke, &q, KeAbs);
     if (rc) { if (err_elem) *err_elem = e; if (err_qp) *err_qp = q; break; }
     int64_t off = e * nval;                                     /* assembleElement assembler.go:79-92 */
     for (int i = 0; i < nd; i++)
-      for (int j = 0; j < nd; j++) { V[off + i * nd + j] = Ke[i * nd + j]; I[off + i * nd + j] = dofs[i]; J[off + i * nd + j] = dofs[j]; }
+      for (int j = 0; j < nd; j++) { V[off + i * nd + j] = Ke[i * nd + j]; if (track) Vabs[off + i * nd + j] = KeAbs[i * nd + j]; I[off + i * nd + j] = dofs[i]; J[off + i * nd + j] = dofs[j]; }
   }
-  if (!rc) accumulate(ga, I, J, V, total);                      /* :118-121: K untouched on error */
-  free(I); free(J); free(V); free(aux1); free(aux2); free(Ke); free(t);
+  if (!rc) accumulate(ga, I, J, V, track ? Vabs : 0, total);                      /* :118-121: K untouched on error */
+  free(I); free(J); free(V); free(Vabs); free(KeAbs); free(aux1); free(aux2); free(Ke); free(t);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   ga->last_seconds = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
   return rc;
@@ -463,7 +533,7 @@ int femo_element_matrices(const double *nodes3, int64_t n_nodes, int kind, int q
     if (rc) { if (err_elem) *err_elem = e; break; }
     store_elem_node(X, nodes3, elem, nn, t->d);
     int q = -1;
-    rc = element_ke(t, X, B, aux1, aux2, KeOut + e * (int64_t)nd * nd, &q);
+    rc = element_ke(t, X, B, aux1, aux2, KeOut + e * (int64_t)nd * nd, &q, 0);
     if (rc) { if (err_elem) *err_elem = e; if (err_qp) *err_qp = q; }
   }
   free(aux1); free(aux2); free(t);

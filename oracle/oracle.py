@@ -79,6 +79,11 @@ class OracleError(Exception):
         super().__init__(f"oracle error {ERR_NAMES.get(kind, kind)} elem={elem} qp={qp}")
 
 
+def set_normaliser(on):
+    """Test-only s_ij bookkeeping on/off (off for timed cpu_baseline runs)."""
+    lib().femo_set_normaliser(int(on))
+
+
 def len_nodes(kind):
     return lib().femo_elem_len_nodes(kind)
 

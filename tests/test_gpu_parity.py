@@ -79,12 +79,25 @@ def test_plane_kinds_match_oracle(pkg, O, meshes, name, mode, flags):
     compare_csr(got, ref, ab, TOL)
 
 
-@pytest.mark.parametrize("name,mode,size", [("hexa8", 4, 4), ("tetra4", 4, 4), ("tetra10", 4, 2), ("hexa20", 4, 2), ("quad4", 5, 9),
+@pytest.mark.parametrize("name,mode,size", [("hexa8", 4, 4), ("tetra10", 4, 2), ("hexa20", 4, 2), ("quad4", 5, 9),
                                             ("quad8", 6, 6), ("triangle3", 6, 7), ("quad4", 6, 9)])
 def test_thermal_kinds_match_oracle(pkg, O, meshes, name, mode, size):
     nodes, conn = meshes.mesh_for(name, size)
     _, got, ref, ab = assemble_both(pkg, O, name, nodes, conn, mode, 1, 45.0, 0.0, node_dofs=1)
     compare_csr(got, ref, ab, TOL)
+
+
+def test_tetra4_cannot_be_thermal(pkg, O, meshes):
+    """Tetra4.Dofs() ignores NodeDofs (tetra4.go:18-20), so a 1-dof thermal model is rejected by mapdofs."""
+    nodes, conn = meshes.bcc_tetra4(2)
+    ga = pkg.fem.NewGeneralAssembler(nodes, 1)
+    err = ga.AddIsoparametric(pkg.elements.Tetra4(NodeDofs=1), pkg.solids.IsotropicConductivity(45.0).Solid3D(), len(conn), conn)
+    assert err.msg == "model dofs 1 does not contain all element dofs 123"
+    og = O.GeneralAssembler(nodes, 1)
+    Cm, bk = O.constitutive(4, 45.0)
+    with pytest.raises(O.OracleError) as ei:
+        og.add_isoparametric(O.TETRA4, Cm, bk, conn, node_dofs=1)
+    assert ei.value.kind == 5
 
 
 @pytest.mark.parametrize("name,order", [("hexa8", 1), ("hexa8", 3), ("hexa8", 4), ("quad4", 1), ("quad4", 5), ("quad8", 2), ("triangle3", 3), ("hexa20", 2)])
@@ -162,7 +175,14 @@ def test_errors_report_lowest_element_and_leave_k_untouched(pkg, O, meshes):
     flat = conn.copy()
     flat[11, 3] = flat[11, 2]
     err = ga.AddIsoparametric(pkg.elements.Tetra4(), c, len(flat), flat)
-    assert err.msg == "zero determinant of jacobian of element #11, Check element shape for bad aspect ratio"
+    with pytest.raises(O.OracleError) as ei:
+        og.add_isoparametric(O.TETRA4, Cm, bk, flat)
+    # two identical Jacobian rows: LU gives exactly 0 or +-O(eps) depending on x*(1/x)==1 -- the GPU follows the
+    # reference's LU (unfused), so it lands on the same side as the oracle
+    assert (ei.value.kind, ei.value.elem) in ((2, 11), (1, 11))
+    expect = {2: "zero determinant of jacobian of element #11, Check element shape for bad aspect ratio",
+              1: "negative determinant of jacobian of element #11, Check node ordering"}[ei.value.kind]
+    assert err.msg == expect
     # tiny but valid elements trip the ABSOLUTE 1e-12 threshold too (8-Q3)
     tiny = pkg.fem.NewGeneralAssembler(nodes * 1e-5, 7)
     err = tiny.AddIsoparametric(pkg.elements.Tetra4(), c, len(conn), conn)
