@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- K-assembly throughput of the B200 path on BASELINE.json's config 1.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config tetra4|hexa8|...] [--size S]
+
+A "step" is one full stiffness assembly of the workload mesh: NewGeneralAssembler + AddIsoparametric
+(symbolic phase + numeric phase + deterministic row reduction), exactly what BenchmarkTetra4Assembly times
+(benchmark_test.go:39-47).  Default workload: Tetra4 BCC cube, N=48: 1,299,456 elements / 684,723 dofs,
+solids.Isotropic{E:200e9, Poisson:0.3}.Solid3D().
+
+  value : elements/s with inputs (nodes, int32 connectivity) already resident in HBM, timed with CUDA events
+          on the library's stream, L2 flushed between steps.
+  e2e   : the same through the reference-facing host API with HOST buffers (pinned): H2D of nodes and int64
+          connectivity, assembly, D2H of the full CSR K into pinned host arrays, all inside the timed region.
+  roofline     : dominant kernel (k_numeric_rows: numeric phase fused with the row reduction) against the
+                 measured HBM copy bandwidth of MEASURED_PEAKS.json.
+  cpu_baseline : the CPU oracle (C port of the reference algorithm, single thread like the reference) timed on
+                 this box's host cores on the same workload.
+  --impl reference : the oracle port timed alone (the Go reference cannot be built: no Go toolchain).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+WORKLOADS = {
+    # name: (mesh kind, default size, element class, constituter, model dofs flag, oracle kind, oracle mode, description)
+    "tetra4": ("tetra4", 48, "Tetra4", ("Isotropic", "Solid3D"), 7, 0, 0, "Tetra4 BCC cube N={s}: {ne} elements / {nd} dofs, Isotropic(E=200e9, nu=0.3).Solid3D"),
+    "quad4": ("quad4", 2000, "Quad4", ("Isotropic", "Axisymmetric"), 3, 4, 1, "Quad4 axisymmetric {s}x{s}: {ne} elements / {nd} dofs"),
+    "hexa8": ("hexa8", 100, "Hexa8", ("Isotropic", "Solid3D"), 7, 2, 0, "Hexa8 brick {s}^3: {ne} elements / {nd} dofs, 2x2x2 Gauss"),
+    "tetra10": ("tetra10", 40, "Tetra10", ("Isotropic", "Solid3D"), 7, 1, 0, "Tetra10 BCC N={s}: {ne} elements / {nd} dofs, 4-point rule"),
+    "hexa20": ("hexa20", 40, "Hexa20", ("Isotropic", "Solid3D"), 7, 3, 0, "Hexa20 brick {s}^3: {ne} elements / {nd} dofs, 3x3x3 Gauss"),
+}
+E_MOD, NU = 200e9, 0.3
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, size):
+    pkg = entry.load_package()
+    from importlib import import_module
+    meshes = import_module("gofem_b200.meshes")
+    kind, dsize, ecls, (mcls, mmeth), flags, okind, omode, desc = WORKLOADS[name]
+    s = size or dsize
+    nodes, conn = meshes.mesh_for(kind, s)
+    elemT = getattr(pkg.elements, ecls)()
+    c = getattr(getattr(pkg.solids, mcls)(E_MOD, NU), mmeth)()
+    ndn = bin(flags).count("1")
+    return dict(pkg=pkg, nodes=nodes, conn=conn, elemT=elemT, c=c, flags=flags, ndn=ndn, okind=okind, omode=omode,
+                desc=desc.format(s=s, ne=conn.shape[0], nd=nodes.shape[0] * ndn), size=s, name=name)
+
+
+def algorithmic_bytes(w, nnz):
+    """Per-launch algorithmic bytes of the dominant kernel (numeric phase + row reduction), DESIGN.md 'Roofline':
+    int32 connectivity + node coordinates + incidence list (n2e_t) + element->slot map (pos16) read,
+    CSR values written."""
+    ne, nn = w["conn"].shape
+    return 4 * nn * ne + 24 * w["nodes"].shape[0] + 4 * nn * ne + 2 * nn * nn * ne + 8 * nnz
+
+
+def cpu_port_seconds(w, nodes, conn):
+    O = entry.load_oracle()
+    O.build()
+    O.set_normaliser(False)          # the reference computes no test normaliser
+    Cm, bk = O.constitutive(w["omode"], E_MOD, NU)
+    og = O.GeneralAssembler(nodes, w["flags"])
+    t0 = time.perf_counter()
+    og.add_isoparametric(w["okind"], Cm, bk, conn)
+    dt = time.perf_counter() - t0
+    O.set_normaliser(True)
+    return dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Go original cannot be built here) timed
+    alone on the host.  Single thread: the reference is one sequential loop (fem.go:140)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.config
+    size = args.size or {"tetra4": 32, "quad4": 700, "hexa8": 40, "tetra10": 16, "hexa20": 12}[name]
+    w = make_workload(name, size)
+    full = make_workload_desc(name, args.size)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_port_seconds(w, w["nodes"], w["conn"])
+        if i >= args.warmup:
+            times.append(dt)
+    ne = w["conn"].shape[0]
+    v = ne * len(times) / sum(times)
+    go_probe = subprocess.run("go version", shell=True, capture_output=True, text=True)
+    line = {"impl": "reference", "metric": "K assembly elements/s", "value": v, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": full, "sample": w["desc"]},
+            "cpu_baseline": {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
+                             "sample": f"{w['desc']} ({ne} elements per step); C port of the reference algorithm incl. full COO + sort-accumulate; go toolchain: "
+                                       + ("present but modules unavailable offline" if go_probe.returncode == 0 else "absent")},
+            "dofs_per_s": v * w["nodes"].shape[0] * w["ndn"] / ne,
+            "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def make_workload_desc(name, size):
+    kind, dsize, *_rest, desc = WORKLOADS[name]
+    s = size or dsize
+    if name == "tetra4":
+        return desc.format(s=s, ne=12 * s * s * (s - 1), nd=3 * ((s + 1) ** 3 + s ** 3))
+    return desc.format(s=s, ne="?", nd="?")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="tetra4", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the assembly path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    warmup = max(args.warmup, 3)
+
+    w = make_workload(args.config, args.size)
+    pkg = w["pkg"]
+    nodes, conn = w["nodes"], w["conn"]
+    ne, nn = conn.shape
+    ndof = nodes.shape[0] * w["ndn"]
+
+    # ---- device-resident inputs (value) -----------------------------------------------------------
+    d_nodes = torch.from_numpy(nodes).to(dev)
+    d_conn = torch.from_numpy(conn.astype(np.int32)).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    L = pkg.lib()
+
+    def one_resident_step():
+        ra = pkg.RawAssembler(None, w["ndn"], device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=nodes.shape[0])
+        desc = ra.make_desc(w["elemT"], w["c"])
+        rc = ra.add(desc, conn_ptr=d_conn.data_ptr(), n_elem=ne, is64=False, on_device=True)
+        if rc:
+            raise RuntimeError(f"femb200_add_isoparametric -> {rc} {ra.last_error()}")
+        return ra
+
+    # one context reused across steps (the memory pool keeps blocks, like a long-lived Go process)
+    ctx_holder = pkg.RawAssembler(None, w["ndn"], device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=nodes.shape[0])
+    import ctypes as C
+
+    def resident_step_shared_ctx():
+        h = C.c_void_p()
+        rc = L.femb200_assembler_create(ctx_holder.ctx, C.c_void_p(d_nodes.data_ptr()), nodes.shape[0], w["ndn"], 1, C.byref(h))
+        assert rc == 0
+        rc = L.femb200_add_isoparametric(h, C.byref(desc0), C.c_void_p(d_conn.data_ptr()), 0, 1, ne)
+        if rc:
+            raise RuntimeError(f"femb200_add_isoparametric -> {rc}")
+        ph = (C.c_float * pkg.N_TIMERS)()
+        L.femb200_phase_ms(h, ph)
+        nnz = L.femb200_nnz(h)
+        L.femb200_assembler_destroy(h)
+        return [float(x) for x in ph], nnz
+
+    desc0 = ctx_holder.make_desc(w["elemT"], w["c"])
+    for _ in range(warmup):
+        resident_step_shared_ctx()
+        flush.fill_(1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.femb200_kernel_launches(ctx_holder.ctx)
+    phases, wall = [], []
+    for _ in range(args.steps):
+        flush.fill_(1)                     # L2 flush between timed iterations (outside the timed region)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ph, nnz = resident_step_shared_ctx()   # returns after the library synchronised its stream
+        wall.append(time.perf_counter() - t0)
+        phases.append(ph)
+    torch.cuda.synchronize()
+    launches = L.femb200_kernel_launches(ctx_holder.ctx) - launches0
+    clocks = sampler.finish()
+    ph_mean = np.mean(np.array(phases), axis=0)
+    dev_ms = float(ph_mean[6])             # CUDA-event time of the whole call on the library's stream
+    t_dev = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t_dev.item())
+    value = world * ne / (dev_ms_max * 1e-3)
+
+    # ---- end to end through the host API with host buffers ------------------------------------------
+    h_nodes = torch.from_numpy(nodes).pin_memory()
+    h_conn = torch.from_numpy(conn).pin_memory()          # int64: a Go []int
+    h_indptr = torch.empty(ndof + 1, dtype=torch.int64).pin_memory()
+    h_indices = torch.empty(nnz, dtype=torch.int32).pin_memory()
+    h_values = torch.empty(nnz, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        h = C.c_void_p()
+        rc = L.femb200_assembler_create(ctx_holder.ctx, C.c_void_p(h_nodes.data_ptr()), nodes.shape[0], w["ndn"], 0, C.byref(h))
+        assert rc == 0
+        rc = L.femb200_add_isoparametric(h, C.byref(desc0), C.c_void_p(h_conn.data_ptr()), 1, 0, ne)
+        assert rc == 0, rc
+        rc = L.femb200_csr_copy(h, C.c_void_p(h_indptr.data_ptr()), C.c_void_p(h_indices.data_ptr()), C.c_void_p(h_values.data_ptr()))
+        assert rc == 0
+        L.femb200_assembler_destroy(h)
+
+    for _ in range(warmup):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_t = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_t.append(time.perf_counter() - t0)
+    t_e2e = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * ne / float(t_e2e.item())
+    h2d = nodes.nbytes + conn.nbytes
+    d2h = h_indptr.numel() * 8 + h_indices.numel() * 4 + h_values.numel() * 8
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    kern_ms = float(ph_mean[4])
+    abytes = algorithmic_bytes(w, nnz)
+    achieved = abytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_numeric_rows (numeric phase fused with the deterministic row reduction)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes": abytes, "kernel_ms": kern_ms,
+                "kernel_share_of_step": kern_ms / dev_ms}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_numeric_rows.json")
+    if os.path.exists(traffic_file):
+        roofline["traffic"] = json.load(open(traffic_file)).get(args.config)
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt = cpu_port_seconds(w, nodes, conn)
+        cpu = {"value": ne / dt, "unit": "elements/s", "cores": 1, "kind": "port",
+               "sample": f"full workload once ({ne} elements, {dt:.1f} s): C port of the reference algorithm (dense per-element Ke, "
+                         f"nd^2 COO triplets, sort + in-order accumulate), single thread like the reference's loop (fem.go:140); "
+                         f"host cpus={os.cpu_count()}"}
+
+    if rank == 0:
+        line = {"metric": "K assembly elements/s", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["desc"], "l2": "flushed between timed steps (256 MiB write)", "inputs": "nodes f64 + int32 connectivity resident in HBM",
+                           "multi_gpu": "replicas (one full mesh per rank)" if world > 1 else "single GPU"},
+                "dofs_per_s": value * ndof / ne,
+                "wall_ms_per_step_host_clock": 1e3 * float(np.mean(wall)),
+                "phases_ms": dict(zip(pkg.TIMER_NAMES, [float(x) for x in ph_mean])),
+                "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * float(t_e2e.item())},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "published_go_reference": {"elements_per_s": 39380, "hardware": "AMD Ryzen 5 3400G, README.md:86 (33.0 s for this mesh)"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
