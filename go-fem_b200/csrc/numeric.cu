@@ -366,6 +366,256 @@ k_numeric_rows(const NumArgs a) {
   }
 }
 
+// =====================================================================================================
+// Two-kernel numeric path (default for every element type):
+//
+//  k_geometry  -- "one batched per-element kernel": one thread per element evaluates, per quadrature
+//                 point, jac = dN*X, det (LU), the reference's error checks, J^-1 dN and the scale, and stages
+//                 the node values v_b[q] (see BT) plus f[q] = dJac*w*scale:  REC = nn*NV + 1 doubles per (e,q).
+//                 Errors are detected here, in element order (atomicMin on the packed error word).
+//  k_rows_dof  -- deterministic row reduction fused with the B^T C B products: one thread per scalar CSR row
+//                 (see the comment on the kernel).
+// Compared with the thread-per-node-row kernel above: NDN x more threads, NDN x less shared memory per
+// thread, no coordinate gathers or geometry in the row loop, no duplicated FP64 work.
+// =====================================================================================================
+template <int D, int NN, int BKIND, bool TAB_CONST>
+__global__ void __launch_bounds__(128)
+k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__restrict__ conn, double *__restrict__ stag,
+           unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp) {
+  using B = BT<BKIND, D>;
+  constexpr int NV = B::NV, REC = (NN * NV + 2) & ~1; // even: 16-byte aligned records
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  Tab<TAB_CONST> tab{tab_g, offW, offN, offDN};
+  double X[NN][D];
+#pragma unroll
+  for (int b = 0; b < NN; ++b) {
+    const int64_t nb = __ldg(conn + e * NN + b);
+#pragma unroll
+    for (int j = 0; j < D; ++j) X[b][j] = __ldg(nodes + nb * 3 + j);
+  }
+  for (int q = 0; q < nqp; ++q) {
+    double inv[D][D], detJ, rinv, scale;
+    const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
+    double *rec = stag + (e * nqp + q) * REC;
+    if (ek) {
+      atomicMin(err, pack_error(e, q, ek));
+      for (int m = 0; m < REC; ++m) rec[m] = 0.0;
+      return; // the reference stops at the first failing quadrature point of the element (:95-107)
+    }
+#pragma unroll
+    for (int b = 0; b < NN; ++b) {
+      double vb[NV];
+      node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) rec[b * NV + v] = vb[v];
+    }
+    rec[NN * NV] = detJ * tab.w(q) * scale; // (dJac*w)*scale, left to right (:111)
+  }
+}
+
+struct DofArgs {
+  int64_t n_rows;             // n_nodes * NDN scalar rows
+  const int32_t *n2e_ptr;
+  const uint32_t *n2e_t;
+  const uint16_t *pos16;
+  const int64_t *blkptr;
+  const double *stag;
+  double *values;
+  const double *tab_g;
+  int nqp;
+};
+
+// One thread per SCALAR CSR row r = NDN*I + i.  The thread walks the elements incident to node I in
+// ascending element index and adds row i of every block (a, b), b = 0..nn-1:
+//     row_i(Ke[a][b]) = sum_q  (f * B_a[:, i]^T C)  B_b          (1 x NDN)
+// B_a[:, i] has at most NZ non-zeros, so the thread keeps the NZ rows of C it needs in registers for the
+// whole kernel (its i never changes) and E = f B_a[:,i]^T C costs NZ*DIMC FMAs, each block row NDN*<=3.
+// No work is duplicated between threads, no two threads ever touch the same accumulator (=> no atomics,
+// no barriers), and every K entry is summed in ascending element order: a deterministic segmented
+// reduction whose segments are the CSR rows.  Accumulators live in shared memory, interleaved by thread
+// (index m*T + tid): conflict free whatever column position each lane hits.
+template <int D, int NN, int BKIND, bool TAB_CONST, int TPB>
+__global__ void __launch_bounds__(TPB)
+k_rows_dof(const DofArgs a) {
+  using B = BT<BKIND, D>;
+  constexpr int NDN = B::NDN, NV = B::NV, DIMC = B::DIMC, REC = (NN * NV + 2) & ~1, NPAIR = REC / 2;
+  constexpr int NZ = (BKIND == FEMB200_B_THERMAL || BKIND == FEMB200_B_THERMAL_AXISYM) ? DIMC : (BKIND == FEMB200_B_PLANE ? 2 : 3);
+  extern __shared__ double s_R[];
+  Tab<TAB_CONST> tab{a.tab_g, 0, 0, 0};
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int64_t r = (int64_t)blockIdx.x * T + tid;
+  if (r >= a.n_rows) return;
+  const int64_t I = r / NDN;
+  const int i = (int)(r - I * NDN);
+  // non-zeros of column i of a node's B block: rows krow[m], value source ksrc[m] (index into v[])
+  int ksrc[NZ];
+  double Cr[NZ][DIMC];
+  {
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < DIMC; ++k) {
+      int sk = -1;
+#pragma unroll
+      for (int ii = 0; ii < NDN; ++ii) if (ii == i) sk = B::sel(k, ii);
+      if (sk >= 0 && m < NZ) {
+        // m is only known at run time (depends on i): write through a predicated unrolled select
+#pragma unroll
+        for (int mm = 0; mm < NZ; ++mm)
+          if (mm == m) {
+            ksrc[mm] = sk;
+#pragma unroll
+            for (int c = 0; c < DIMC; ++c) Cr[mm][c] = tab.template C<DIMC>(k, c);
+          }
+        ++m;
+      }
+    }
+#pragma unroll
+    for (int mm = 0; mm < NZ; ++mm)
+      if (mm >= m) {
+        ksrc[mm] = -1;
+#pragma unroll
+        for (int c = 0; c < DIMC; ++c) Cr[mm][c] = 0.0;
+      }
+  }
+  const int beg = a.n2e_ptr[I], end = a.n2e_ptr[I + 1];
+  const int64_t b0 = a.blkptr[I];
+  const int rl = (int)(a.blkptr[I + 1] - b0);
+  const int rowsz = rl * NDN;
+  for (int m = 0; m < rowsz; ++m) s_R[m * T + tid] = 0.0;
+  for (int k = beg; k < end; ++k) {
+    const uint32_t t = __ldg(a.n2e_t + k);
+    const int64_t e = t / NN;
+    const int la = (int)(t % NN);
+    // row-local slot positions of the element's nn nodes (the element->slot map), vector loads when aligned
+    int pos[NN];
+    if constexpr (NN % 4 == 0) {
+      const uint2 *pk2 = reinterpret_cast<const uint2 *>(a.pos16 + (int64_t)k * NN);
+#pragma unroll
+      for (int v4 = 0; v4 < NN / 4; ++v4) {
+        const uint2 w = __ldg(pk2 + v4);
+        pos[4 * v4] = w.x & 0xffff; pos[4 * v4 + 1] = w.x >> 16; pos[4 * v4 + 2] = w.y & 0xffff; pos[4 * v4 + 3] = w.y >> 16;
+      }
+    } else {
+      const uint16_t *pk = a.pos16 + (int64_t)k * NN;
+#pragma unroll
+      for (int b = 0; b < NN; ++b) pos[b] = __ldg(pk + b);
+    }
+    double acc[NN][NDN];
+#pragma unroll
+    for (int b = 0; b < NN; ++b)
+#pragma unroll
+      for (int j = 0; j < NDN; ++j) acc[b][j] = 0.0;
+    const double *rec = a.stag + e * a.nqp * REC;
+    for (int q = 0; q < a.nqp; ++q, rec += REC) {
+      // the whole record with 16-byte loads: [v_0 .. v_{nn-1} | f | pad]
+      double rv[REC];
+      const double2 *rec2 = reinterpret_cast<const double2 *>(rec);
+#pragma unroll
+      for (int c2 = 0; c2 < NPAIR; ++c2) {
+        const double2 w = __ldg(rec2 + c2);
+        rv[2 * c2] = w.x; rv[2 * c2 + 1] = w.y;
+      }
+      const double f = rv[NN * NV];
+      double E[DIMC];
+#pragma unroll
+      for (int c = 0; c < DIMC; ++c) E[c] = 0.0;
+#pragma unroll
+      for (int m = 0; m < NZ; ++m) {
+        const double u = (ksrc[m] >= 0) ? __ldg(rec + la * NV + ksrc[m]) * f : 0.0; // run-time index: separate (L1-hit) load
+#pragma unroll
+        for (int c = 0; c < DIMC; ++c) E[c] = fma(u, Cr[m][c], E[c]);
+      }
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+#pragma unroll
+        for (int j = 0; j < NDN; ++j) {
+          double sj = acc[b][j];
+#pragma unroll
+          for (int kk = 0; kk < DIMC; ++kk)
+            if (B::sel(kk, j) >= 0) sj = fma(E[kk], rv[b * NV + B::sel(kk, j)], sj);
+          acc[b][j] = sj;
+        }
+      }
+    }
+    // Ordered accumulation.  The nn column blocks of one element are distinct unless the element is
+    // collapsed (a repeated node); when they are distinct all read-modify-writes are issued as one batch
+    // (loads, adds, stores) instead of nn dependent chains the compiler must assume may alias.
+    bool distinct = true;
+    if constexpr (NN <= 8) {
+#pragma unroll
+      for (int b = 1; b < NN; ++b)
+#pragma unroll
+        for (int c = 0; c < b; ++c) distinct = distinct && (pos[b] != pos[c]);
+    } else {
+      distinct = false;
+    }
+    if (distinct) {
+      double old[NN][NDN];
+#pragma unroll
+      for (int b = 0; b < NN; ++b)
+#pragma unroll
+        for (int j = 0; j < NDN; ++j) old[b][j] = s_R[(pos[b] * NDN + j) * T + tid];
+#pragma unroll
+      for (int b = 0; b < NN; ++b)
+#pragma unroll
+        for (int j = 0; j < NDN; ++j) s_R[(pos[b] * NDN + j) * T + tid] = old[b][j] + acc[b][j];
+    } else {
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+        double old[NDN];
+#pragma unroll
+        for (int j = 0; j < NDN; ++j) old[j] = s_R[(pos[b] * NDN + j) * T + tid];
+#pragma unroll
+        for (int j = 0; j < NDN; ++j) s_R[(pos[b] * NDN + j) * T + tid] = old[j] + acc[b][j];
+      }
+    }
+  }
+  double *const vrow = a.values + (int64_t)NDN * NDN * b0 + (int64_t)i * rowsz;
+  for (int m = 0; m < rowsz; ++m) vrow[m] = s_R[m * T + tid];
+}
+
+template <int D, int NN, int BKIND, bool TAB_CONST>
+static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32, int64_t n_elem,
+                        SymbolicResult *sym) {
+  femb200_ctx *ctx = ga->ctx;
+  using B = BT<BKIND, D>;
+  constexpr int REC = (NN * B::NV + 2) & ~1;
+  constexpr int TPB = 128;
+  const size_t per_thread = (size_t)sym->max_rowlen * B::NDN * sizeof(double);
+  auto rows = k_rows_dof<D, NN, BKIND, TAB_CONST, TPB>;
+  FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  int bestT = 0, best_threads = 0;
+  const int cands[4] = {128, 96, 64, 32};
+  for (int c = 0; c < 4; ++c) {
+    const size_t need = per_thread * cands[c];
+    if (need > ctx->smem_optin) continue;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rows, cands[c], need) != cudaSuccess) continue;
+    if (nb * cands[c] > best_threads) { best_threads = nb * cands[c]; bestT = cands[c]; }
+  }
+  if (bestT == 0) return -2;
+  TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
+  double *stag = nullptr;
+  int rc = dev_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * REC);
+  if (rc) return rc;
+  if (n_elem) {
+    k_geometry<D, NN, BKIND, TAB_CONST><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, ga->d_nodes, conn32, stag, ctx->d_err, d_tab,
+                                                                                      tl.offW, tl.offN, tl.offDN, sh.nqp);
+    ctx->launches++;
+  }
+  DofArgs a;
+  a.n_rows = ga->n_nodes * B::NDN; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
+  a.stag = stag; a.values = sym->csr.values; a.tab_g = d_tab; a.nqp = sh.nqp;
+  if (a.n_rows) {
+    rows<<<grid_for(a.n_rows, bestT), bestT, per_thread * bestT, ctx->stream>>>(a);
+    ctx->launches++;
+  }
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  dev_free(ctx, stag);
+  return 0;
+}
+
 // ---- launch plumbing -------------------------------------------------------------------------------
 template <int D, int NN, int BKIND, bool SMEM_ACC, bool TAB_CONST>
 static int launch_rows_T(femb200_ctx *ctx, const NumArgs &a, int max_rowlen) {
@@ -399,12 +649,18 @@ static int launch_rows_T(femb200_ctx *ctx, const NumArgs &a, int max_rowlen) {
 }
 
 template <int D, int NN, int BKIND>
-static int launch_rows(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, bool tab_const, SymbolicResult *sym) {
+static int launch_rows(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, bool tab_const, SymbolicResult *sym, int64_t n_elem) {
   femb200_ctx *ctx = ga->ctx;
   using B = BT<BKIND, D>;
   if (sh.ndn != B::NDN || sh.dimC != B::DIMC) return FEMB200_ERR_UNSUPPORTED;
   int rc = -2;
   const bool force_global = getenv("FEMB200_FORCE_GLOBAL_ACC") != nullptr;
+  const bool force_thread_rows = getenv("FEMB200_FORCE_THREAD_ROWS") != nullptr;
+  if (sh.identity && !force_global && !force_thread_rows) {
+    rc = tab_const ? launch_dof_T<D, NN, BKIND, true>(ga, sh, a.tab_g, a.conn, n_elem, sym)
+                   : launch_dof_T<D, NN, BKIND, false>(ga, sh, a.tab_g, a.conn, n_elem, sym);
+    if (rc != -2) return rc;
+  }
   if (sh.identity && !force_global)
     rc = tab_const ? launch_rows_T<D, NN, BKIND, true, true>(ctx, a, sym->max_rowlen)
                    : launch_rows_T<D, NN, BKIND, true, false>(ctx, a, sym->max_rowlen);
@@ -417,19 +673,19 @@ static int launch_rows(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, b
 }
 
 template <int D, int BKIND>
-static int dispatch_nn(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, bool tc, SymbolicResult *sym) {
+static int dispatch_nn(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, bool tc, SymbolicResult *sym, int64_t n_elem) {
   if (D == 3) {
     switch (sh.nn) {
-    case 4: return launch_rows<D, 4, BKIND>(ga, sh, a, tc, sym);
-    case 8: return launch_rows<D, 8, BKIND>(ga, sh, a, tc, sym);
-    case 10: return launch_rows<D, 10, BKIND>(ga, sh, a, tc, sym);
-    case 20: return launch_rows<D, 20, BKIND>(ga, sh, a, tc, sym);
+    case 4: return launch_rows<D, 4, BKIND>(ga, sh, a, tc, sym, n_elem);
+    case 8: return launch_rows<D, 8, BKIND>(ga, sh, a, tc, sym, n_elem);
+    case 10: return launch_rows<D, 10, BKIND>(ga, sh, a, tc, sym, n_elem);
+    case 20: return launch_rows<D, 20, BKIND>(ga, sh, a, tc, sym, n_elem);
     }
   } else {
     switch (sh.nn) {
-    case 3: return launch_rows<D, 3, BKIND>(ga, sh, a, tc, sym);
-    case 4: return launch_rows<D, 4, BKIND>(ga, sh, a, tc, sym);
-    case 8: return launch_rows<D, 8, BKIND>(ga, sh, a, tc, sym);
+    case 3: return launch_rows<D, 3, BKIND>(ga, sh, a, tc, sym, n_elem);
+    case 4: return launch_rows<D, 4, BKIND>(ga, sh, a, tc, sym, n_elem);
+    case 8: return launch_rows<D, 8, BKIND>(ga, sh, a, tc, sym, n_elem);
     }
   }
   return FEMB200_ERR_UNSUPPORTED;
@@ -471,13 +727,13 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
   a.nu = sh.nu;
   for (int i = 0; i < kMaxNdn; ++i) a.dof2u[i] = sh.dof2u[i];
   switch (sh.bkind) {
-  case FEMB200_B_XYZ: return dispatch_nn<3, FEMB200_B_XYZ>(ga, sh, a, tab_const, sym);
-  case FEMB200_B_PLANE: return dispatch_nn<2, FEMB200_B_PLANE>(ga, sh, a, tab_const, sym);
-  case FEMB200_B_AXISYM: return dispatch_nn<2, FEMB200_B_AXISYM>(ga, sh, a, tab_const, sym);
+  case FEMB200_B_XYZ: return dispatch_nn<3, FEMB200_B_XYZ>(ga, sh, a, tab_const, sym, n_elem);
+  case FEMB200_B_PLANE: return dispatch_nn<2, FEMB200_B_PLANE>(ga, sh, a, tab_const, sym, n_elem);
+  case FEMB200_B_AXISYM: return dispatch_nn<2, FEMB200_B_AXISYM>(ga, sh, a, tab_const, sym, n_elem);
   case FEMB200_B_THERMAL:
-    return sh.d == 3 ? dispatch_nn<3, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym)
-                     : dispatch_nn<2, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym);
-  case FEMB200_B_THERMAL_AXISYM: return dispatch_nn<2, FEMB200_B_THERMAL_AXISYM>(ga, sh, a, tab_const, sym);
+    return sh.d == 3 ? dispatch_nn<3, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym, n_elem)
+                     : dispatch_nn<2, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym, n_elem);
+  case FEMB200_B_THERMAL_AXISYM: return dispatch_nn<2, FEMB200_B_THERMAL_AXISYM>(ga, sh, a, tab_const, sym, n_elem);
   }
   return FEMB200_ERR_UNSUPPORTED;
 }

@@ -7,7 +7,8 @@
 // NODE-BLOCK granularity (nn^2 pairs per element instead of nd^2) and expanded once.
 //
 //   conn[e][a]                      --histogram+scan-->  n2e_ptr[node]
-//   (key=node, val=t=e*nn+a)        --radix sort----->   n2e_t grouped by node, t ascending (stable)
+//   t = e*nn+a                      --atomic cursor-->   n2e_t grouped by node (lists sorted ascending by the
+//                                                        pattern kernel => deterministic, ascending element)
 //   per row node I                  --sorted insert-->   column nodes of row I (ascending), rowlen[I]
 //   second sweep over the incidences ---------------->   pos16[k][b] = position of node b of e in row I
 //   scan(rowlen) -> blkptr;  expand -> indptr (int64), indices (int32)
@@ -43,12 +44,22 @@ int narrow_and_validate_conn(femb200_assembler *ga, const void *d_in, bool is64,
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void k_count_incidence(const int32_t *__restrict__ conn, int64_t n, int32_t *__restrict__ cnt,
-                                  uint32_t *__restrict__ iota) {
+__global__ void k_count_incidence(const int32_t *__restrict__ conn, int64_t n, int32_t *__restrict__ cnt) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   atomicAdd(&cnt[conn[t]], 1);
-  iota[t] = (uint32_t)t;
+}
+
+// Incidence lists by atomic cursor: n2e_t[n2e_ptr[node] + slot] = t.  The slot order depends on the atomics'
+// arrival order; every list is sorted (ascending t = ascending element) by the row-pattern kernel that
+// consumes it, which is what makes the later row reduction deterministic.
+__global__ void k_fill_incidence(const int32_t *__restrict__ conn, int64_t n, const int32_t *__restrict__ n2e_ptr,
+                                 int32_t *__restrict__ cursor, uint32_t *__restrict__ n2e_t) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int32_t node = conn[t];
+  const int slot = atomicAdd(&cursor[node], 1);
+  n2e_t[n2e_ptr[node] + slot] = (uint32_t)t;
 }
 
 // One thread per row node: builds the ascending list of distinct column nodes of the node-block row.
@@ -56,14 +67,21 @@ __global__ void k_count_incidence(const int32_t *__restrict__ conn, int64_t n, i
 // thread's private slice of `tmpcols` (capacity nn * valence >= any possible row length) on overflow.
 template <int NN>
 __global__ void __launch_bounds__(128)
-k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, const uint32_t *__restrict__ n2e_t,
+k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__restrict__ n2e_t,
               const int32_t *__restrict__ conn, int32_t *__restrict__ tmpcols, int64_t *__restrict__ rowlen,
-              uint16_t *__restrict__ pos16, int cap_s, unsigned long long *err) {
+              uint16_t *__restrict__ pos16, int cap_s, unsigned long long *err, int only_flagged) {
   extern __shared__ int32_t s_list[];
   const int T = blockDim.x, tid = threadIdx.x;
   int64_t I = (int64_t)blockIdx.x * T + tid;
   if (I >= n_nodes) return;
+  if (only_flagged && rowlen[I] >= 0) return; // already done by k_row_pattern_group
   const int beg = n2e_ptr[I], end = n2e_ptr[I + 1];
+  for (int a = beg + 1; a < end; ++a) { // incidence list into ascending element order (insertion sort, in place)
+    const uint32_t v = n2e_t[a];
+    int j = a - 1;
+    while (j >= beg && n2e_t[j] > v) { n2e_t[j + 1] = n2e_t[j]; --j; }
+    n2e_t[j + 1] = v;
+  }
   int32_t *gl = tmpcols + (int64_t)NN * beg;
   bool in_s = true;
   int cnt = 0;
@@ -110,6 +128,164 @@ k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, const uint32
 #undef LST_SET
 }
 
+// Fast path of the row pattern: a group of G = 8 lanes per row node.
+//   1. the lanes load the node's (<= 32) incidences in one go and sort them by rank counting in shared
+//      memory (ascending t = ascending element); the sorted list is written back to n2e_t,
+//   2. every lane gathers the connectivity of its incidences (all gathers of the row are in flight at once --
+//      one memory round trip per row instead of one per incident element),
+//   3. the candidate column nodes go into a small open-addressing hash table in shared memory (atomicCAS),
+//   4. the distinct keys are compacted (ballot + popc) and ranked by counting => ascending column list,
+//      each table slot learns its rank,
+//   5. every (incidence, local node) is turned into its row-local slot position with one probe
+//      (the element -> CSR-slot map), written with vector stores.
+// Rows with more than 32 incidences or more than CAP distinct columns are flagged (rowlen = -1) and redone
+// by the sorted-insert kernel k_row_pattern.
+template <int NN, int HS>
+__global__ void __launch_bounds__(256)
+k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__restrict__ n2e_t,
+                    const int32_t *__restrict__ conn, int32_t *__restrict__ tmpcols, int64_t *__restrict__ rowlen,
+                    uint16_t *__restrict__ pos16) {
+  constexpr int G = 8, IPL = 4, MAXINC = G * IPL;
+  constexpr int CAP = HS * 3 / 4;
+  constexpr int LOG = HS == 32 ? 5 : (HS == 64 ? 6 : 7);
+  constexpr int GW = HS + HS + MAXINC + CAP; // 32-bit words of shared memory per group
+  extern __shared__ int32_t s_mem[];
+  const int tid = threadIdx.x, l = tid & (G - 1);
+  int32_t *keys = s_mem + (tid / G) * GW;
+  int32_t *rk = keys + HS;
+  uint32_t *lst = reinterpret_cast<uint32_t *>(rk + HS);
+  int32_t *ul = reinterpret_cast<int32_t *>(lst + MAXINC);
+  const int64_t I = ((int64_t)blockIdx.x * blockDim.x + tid) / G;
+  if (I >= n_nodes) return;
+  const int gshift = (tid & 31) & ~(G - 1);
+  const unsigned gmask = 0xffu << gshift;
+  const int beg = n2e_ptr[I], end = n2e_ptr[I + 1];
+  const int m = end - beg;
+  if (m > MAXINC) { if (l == 0) rowlen[I] = -1; return; }
+
+  // 1. incidences, sorted
+  uint32_t tv[IPL];
+#pragma unroll
+  for (int s = 0; s < IPL; ++s) {
+    const int idx = l + G * s;
+    tv[s] = idx < m ? n2e_t[beg + idx] : 0xffffffffu;
+    if (idx < m) lst[idx] = tv[s];
+  }
+  __syncwarp(gmask);
+#pragma unroll
+  for (int s = 0; s < IPL; ++s) {
+    if (l + G * s < m) {
+      int r = 0;
+      for (int j = 0; j < m; ++j) r += lst[j] < tv[s];
+      rk[r] = (int32_t)tv[s];
+      n2e_t[beg + r] = tv[s];
+    }
+  }
+  __syncwarp(gmask);
+#pragma unroll
+  for (int s = 0; s < IPL; ++s) tv[s] = (l + G * s < m) ? (uint32_t)rk[l + G * s] : 0xffffffffu;
+  __syncwarp(gmask);
+
+  // 2. connectivity of my incidences
+  int32_t cj[IPL][NN];
+#pragma unroll
+  for (int s = 0; s < IPL; ++s) {
+    if (l + G * s < m) {
+      const int32_t *ce = conn + (int64_t)(tv[s] / NN) * NN;
+      if constexpr (NN % 4 == 0) {
+#pragma unroll
+        for (int v4 = 0; v4 < NN / 4; ++v4) {
+          const int4 w = __ldg(reinterpret_cast<const int4 *>(ce) + v4);
+          cj[s][4 * v4] = w.x; cj[s][4 * v4 + 1] = w.y; cj[s][4 * v4 + 2] = w.z; cj[s][4 * v4 + 3] = w.w;
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < NN; ++b) cj[s][b] = __ldg(ce + b);
+      }
+    }
+  }
+
+  // 3. hash insert
+  for (int h = l; h < HS; h += G) keys[h] = -1;
+  __syncwarp(gmask);
+  bool ovf = false;
+#pragma unroll
+  for (int s = 0; s < IPL; ++s) {
+    if (l + G * s < m) {
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+        const int32_t J = cj[s][b];
+        unsigned h = ((unsigned)J * 0x9E3779B1u) >> (32 - LOG);
+        int probe = 0;
+        for (; probe < HS; ++probe) {
+          const int32_t old = atomicCAS(&keys[h], -1, J);
+          if (old == -1 || old == J) break;
+          h = (h + 1) & (HS - 1);
+        }
+        ovf = ovf || (probe == HS);
+      }
+    }
+  }
+  __syncwarp(gmask);
+
+  // 4. compact the distinct keys, rank them
+  int cnt = 0;
+#pragma unroll
+  for (int s = 0; s < HS / G; ++s) {
+    const int32_t key = keys[s * G + l];
+    const bool has = key >= 0;
+    const unsigned bal = (__ballot_sync(gmask, has) >> gshift) & 0xffu;
+    const int off = cnt + __popc(bal & ((1u << l) - 1u));
+    if (has && off < CAP) ul[off] = key;
+    cnt += __popc(bal);
+  }
+  ovf = __any_sync(gmask, ovf) || cnt > CAP;
+  if (ovf) { if (l == 0) rowlen[I] = -1; return; }
+  __syncwarp(gmask);
+  int32_t *gcols = tmpcols + (int64_t)NN * beg;
+#pragma unroll
+  for (int s = 0; s < HS / G; ++s) {
+    const int32_t key = keys[s * G + l];
+    if (key >= 0) {
+      int r = 0;
+      for (int j = 0; j < cnt; ++j) r += ul[j] < key;
+      rk[s * G + l] = r;
+      gcols[r] = key;
+    }
+  }
+  __syncwarp(gmask);
+
+  // 5. element -> slot positions
+#pragma unroll
+  for (int s = 0; s < IPL; ++s) {
+    const int idx = l + G * s;
+    if (idx < m) {
+      int pb[NN];
+#pragma unroll
+      for (int b = 0; b < NN; ++b) {
+        const int32_t J = cj[s][b];
+        unsigned h = ((unsigned)J * 0x9E3779B1u) >> (32 - LOG);
+        while (keys[h] != J) h = (h + 1) & (HS - 1);
+        pb[b] = rk[h];
+      }
+      uint16_t *pk = pos16 + (int64_t)(beg + idx) * NN;
+      if constexpr (NN % 4 == 0) {
+#pragma unroll
+        for (int v4 = 0; v4 < NN / 4; ++v4) {
+          uint2 w;
+          w.x = (unsigned)pb[4 * v4] | ((unsigned)pb[4 * v4 + 1] << 16);
+          w.y = (unsigned)pb[4 * v4 + 2] | ((unsigned)pb[4 * v4 + 3] << 16);
+          reinterpret_cast<uint2 *>(pk)[v4] = w;
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < NN; ++b) pk[b] = (uint16_t)pb[b];
+      }
+    }
+  }
+  if (l == 0) rowlen[I] = cnt;
+}
+
 // scalar row pointers: row (I, m), m in [0, mdpn)
 __global__ void k_indptr(int64_t n_nodes, int mdpn, int nu, unsigned umask, const int64_t *__restrict__ blkptr,
                          int64_t *__restrict__ indptr) {
@@ -149,14 +325,24 @@ __global__ void k_expand(int64_t n_nodes, int64_t nblk, int nn, int mdpn, int nu
 }
 
 template <int NN>
-static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *n2e_ptr, const uint32_t *n2e_t,
+static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *n2e_ptr, uint32_t *n2e_t,
                               const int32_t *conn, int32_t *tmpcols, int64_t *rowlen, uint16_t *pos16) {
+  const bool no_hash = getenv("FEMB200_NO_HASH_PATTERN") != nullptr;
+  if (!no_hash) {
+    constexpr int HS = NN <= 4 ? 32 : (NN <= 8 ? 64 : 128);
+    constexpr int GW = HS + HS + 32 + HS * 3 / 4;
+    const int T = 256;
+    const size_t smem = (size_t)(T / 8) * GW * sizeof(int32_t);
+    FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(k_row_pattern_group<NN, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_row_pattern_group<NN, HS><<<grid_for(n_nodes * 8, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16);
+    ctx->launches++;
+  }
   const int T = 128;
-  // room for the longest rows of structured meshes (Hexa20 corner rows have 81 blocks)
+  // sorted-insert fallback: every row when the group path is disabled, else only the rows it flagged
   int cap_s = NN <= 4 ? 48 : (NN <= 8 ? 64 : 96);
   size_t smem = (size_t)cap_s * T * sizeof(int32_t);
   FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(k_row_pattern<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_row_pattern<NN><<<grid_for(n_nodes, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, cap_s, ctx->d_err);
+  k_row_pattern<NN><<<grid_for(n_nodes, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, cap_s, ctx->d_err, no_hash ? 0 : 1);
   ctx->launches++;
   FEMB_CUDA_OK(ctx, cudaGetLastError());
   return 0;
@@ -184,38 +370,31 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
 
   // ---- node -> element adjacency -------------------------------------------------------------
   int32_t *cnt = nullptr;
-  uint32_t *iota = nullptr, *keys_sorted = nullptr;
-  if ((rc = dev_alloc(ctx, &cnt, n_nodes + 1))) return rc;
-  if ((rc = dev_alloc(ctx, &iota, ninc))) return rc;
-  if ((rc = dev_alloc(ctx, &keys_sorted, ninc))) return rc;
+  if ((rc = dev_alloc(ctx, &cnt, 2 * (n_nodes + 1)))) return rc; // histogram | fill cursors
+  int32_t *cursor = cnt + (n_nodes + 1);
   if ((rc = dev_alloc(ctx, &out->n2e_ptr, n_nodes + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->n2e_t, ninc))) return rc;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (n_nodes + 1), st));
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, sizeof(int32_t) * 2 * (n_nodes + 1), st));
   if (ninc) {
-    k_count_incidence<<<grid_for(ninc, 256), 256, 0, st>>>(conn32, ninc, cnt, iota);
+    k_count_incidence<<<grid_for(ninc, 256), 256, 0, st>>>(conn32, ninc, cnt);
     ctx->launches++;
   }
-  size_t tmp1 = 0, tmp2 = 0, tmp3 = 0, tmp4 = 0;
-  int end_bit = 1;
-  while (((int64_t)1 << end_bit) < n_nodes && end_bit < 32) ++end_bit;
+  size_t tmp1 = 0, tmp3 = 0, tmp4 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp1, cnt, out->n2e_ptr, (int)(n_nodes + 1), st);
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (const uint32_t *)conn32, keys_sorted, iota, out->n2e_t, (int)ninc, 0, end_bit, st);
   int64_t *rowlen = nullptr;
   if ((rc = dev_alloc(ctx, &rowlen, n_nodes + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->blkptr, n_nodes + 1))) return rc;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp3, rowlen, out->blkptr, (int)(n_nodes + 1), st);
   cub::DeviceReduce::Max(nullptr, tmp4, rowlen, ctx->d_scalars, (int)(n_nodes + 1), st);
-  size_t tmpmax = tmp1 > tmp2 ? tmp1 : tmp2;
-  if (tmp3 > tmpmax) tmpmax = tmp3;
+  size_t tmpmax = tmp1 > tmp3 ? tmp1 : tmp3;
   if (tmp4 > tmpmax) tmpmax = tmp4;
   if ((rc = ensure_cub_tmp(ctx, tmpmax + 256))) return rc;
   size_t tb = ctx->cub_tmp_bytes;
   FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, cnt, out->n2e_ptr, (int)(n_nodes + 1), st));
   ctx->launches += 2;
   if (ninc) {
-    tb = ctx->cub_tmp_bytes;
-    FEMB_CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tb, (const uint32_t *)conn32, keys_sorted, iota, out->n2e_t, (int)ninc, 0, end_bit, st));
-    ctx->launches += 1 + 2 * ((end_bit + 7) / 8);
+    k_fill_incidence<<<grid_for(ninc, 256), 256, 0, st>>>(conn32, ninc, out->n2e_ptr, cursor, out->n2e_t);
+    ctx->launches++;
   }
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], st));
 
@@ -247,8 +426,6 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   out->max_rowlen = (int)ctx->h_scalars[0];
   out->nblk = ctx->h_scalars[1];
   dev_free(ctx, cnt);
-  dev_free(ctx, iota);
-  dev_free(ctx, keys_sorted);
   dev_free(ctx, rowlen);
   if (*ctx->h_err != kNoError) { dev_free(ctx, tmpcols); return -1; } // caller decodes the error word
   if (out->max_rowlen > 65535) { dev_free(ctx, tmpcols); return FEMB200_ERR_TOO_LARGE; }

@@ -118,6 +118,39 @@ def test_global_accumulator_path_matches(pkg, O, meshes, monkeypatch):
         compare_csr(got, ref, ab, TOL)
 
 
+@pytest.mark.parametrize("env", ["FEMB200_FORCE_THREAD_ROWS", "FEMB200_NO_HASH_PATTERN"])
+def test_alternative_kernel_paths_match(pkg, O, meshes, monkeypatch, env):
+    """The thread-per-row numeric kernel (used for nn > 8) and the sorted-insert pattern kernel (overflow path)
+    stay parity-checked on the low-order elements too."""
+    monkeypatch.setenv(env, "1")
+    for name, size in (("tetra4", 5), ("hexa8", 3), ("quad4", 9), ("triangle3", 6), ("quad8", 4)):
+        nodes, conn = meshes.mesh_for(name, size)
+        k = KINDS[name]
+        _, got, ref, ab = assemble_both(pkg, O, name, nodes, conn, k["mode"], k["flags"])
+        compare_csr(got, ref, ab, TOL)
+
+
+def test_collapsed_element_with_positive_volume_neighbours(pkg, O, meshes):
+    """Quad4 with two coincident node ids (a triangle-shaped quad) is legal: detJ stays > 0 at the Gauss points.
+    Two local nodes then map to the same column block; the group kernel serialises those lanes."""
+    nodes, conn = meshes.quad4_grid(6, 6, jittered=False)
+    conn = conn.copy()
+    conn[7, 3] = conn[7, 2]          # node 3 collapsed onto node 2
+    conn[20, 1] = conn[20, 0]
+    ga = pkg.fem.NewGeneralAssembler(nodes, 3)
+    err = ga.AddIsoparametric(pkg.elements.Quad4(), pkg.solids.Isotropic(1e5, 0.3).PlaneStess(), len(conn), conn)
+    og = O.GeneralAssembler(nodes, 3)
+    Cm, bk = O.constitutive(2, 1e5, 0.3)
+    try:
+        og.add_isoparametric(O.QUAD4, Cm, bk, conn)
+    except O.OracleError as oe:
+        assert err is not None and f"#{oe.elem}" in err.msg
+        return
+    assert err is None, err
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    compare_csr(ga.Ksolid().csr(), (rp, ri, rv), ab, TOL)
+
+
 def test_high_valence_node_long_rows(pkg, O):
     """A fan of 300 triangles around one hub node: the hub row has 301 blocks (spills the shared list)."""
     n = 300
