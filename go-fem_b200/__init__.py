@@ -67,6 +67,11 @@ def lib():
     L.femb200_csr_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.femb200_csr_at.argtypes = [vp, C.c_int64, C.c_int64, _dp]
     L.femb200_csr_matvec.argtypes = [vp, _dp, _dp]
+    L.femb200_csr_accumulate_rows_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    L.femb200_csr_keep_rows_device.argtypes = [vp, vp]
+    L.femb200_assembler_set_node_mask_device.argtypes = [vp, vp]
+    L.femb200_csr_add_entries_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    L.femb200_add_isoparametric_halo.argtypes = [vp, C.POINTER(ElemDesc), vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64]
     L.femb200_last_slot_map.argtypes = [vp, _i64p]
     L.femb200_isoparametric_strains.argtypes = [vp, C.POINTER(ElemDesc), vp, C.c_int32, C.c_int32, C.c_int64, _dp, _dp]
     L.femb200_phase_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -450,7 +455,7 @@ class RawAssembler:
         desc._keep = (N, dN, w, Cm, dm)
         return desc
 
-    def add(self, desc, conn=None, conn_ptr=None, n_elem=None, is64=False, on_device=False):
+    def add(self, desc, conn=None, conn_ptr=None, n_elem=None, is64=False, on_device=False, n_pattern_only=0):
         if conn is not None:
             conn = np.ascontiguousarray(conn)
             is64 = conn.dtype == np.int64
@@ -458,7 +463,7 @@ class RawAssembler:
                 conn = np.ascontiguousarray(conn, dtype=np.int32)
             n_elem = conn.size // desc.nn
             conn_ptr = conn.ctypes.data
-        return lib().femb200_add_isoparametric(self.h, C.byref(desc), C.c_void_p(conn_ptr), int(is64), int(on_device), n_elem)
+        return lib().femb200_add_isoparametric_halo(self.h, C.byref(desc), C.c_void_p(conn_ptr), int(is64), int(on_device), n_elem, n_pattern_only)
 
     def last_error(self):
         k, e, q = C.c_int32(), C.c_int64(), C.c_int32()

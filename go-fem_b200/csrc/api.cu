@@ -187,7 +187,12 @@ static int stage_conn(femb200_assembler *ga, const void *conn, bool is64, bool o
 
 int femb200_add_isoparametric(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn,
                               int32_t conn_is_int64, int32_t conn_on_device, int64_t n_elem) {
-  if (!ga || n_elem < 0 || (n_elem > 0 && !conn)) return FEMB200_ERR_BAD_ARG;
+  return femb200_add_isoparametric_halo(ga, desc, conn, conn_is_int64, conn_on_device, n_elem, 0);
+}
+
+int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn,
+                                   int32_t conn_is_int64, int32_t conn_on_device, int64_t n_elem, int64_t n_pattern_only) {
+  if (!ga || n_elem < 0 || n_pattern_only < 0 || n_pattern_only > n_elem || (n_elem > 0 && !conn)) return FEMB200_ERR_BAD_ARG;
   femb200_ctx *ctx = ga->ctx;
   cudaStream_t st = ctx->stream;
   FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -229,7 +234,7 @@ int femb200_add_isoparametric(femb200_assembler *ga, const femb200_elem_desc *de
   if (rc == -1) rc = decode_error(ga);
   if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; }
 
-  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), conn32, n_elem, &sym);
+  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), conn32, n_elem - n_pattern_only, &sym);
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);
@@ -330,6 +335,36 @@ int femb200_csr_matvec(const femb200_assembler *cga, const double *x, double *y)
   if (!rc) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   dev_free(ctx, dx); dev_free(ctx, dy);
   FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+
+int femb200_csr_accumulate_rows_device(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr,
+                                       const int32_t *indices, const double *values) {
+  if (!ga || n_rows < 0 || (n_rows > 0 && (!rows || !indptr))) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
+  int rc = csr_accumulate_rows(ga, n_rows, rows, indptr, indices, values);
+  cudaStreamSynchronize(ga->ctx->stream);
+  return rc;
+}
+
+int femb200_csr_add_entries_device(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr,
+                                   const int32_t *indices, const double *values) {
+  if (!ga || n_rows < 0 || (n_rows > 0 && (!rows || !indptr))) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
+  return csr_add_entries(ga, n_rows, rows, indptr, indices, values);
+}
+
+int femb200_assembler_set_node_mask_device(femb200_assembler *ga, const uint8_t *node_mask) {
+  if (!ga) return FEMB200_ERR_BAD_ARG;
+  ga->d_node_mask = node_mask;
+  return 0;
+}
+
+int femb200_csr_keep_rows_device(femb200_assembler *ga, const uint8_t *keep) {
+  if (!ga || !keep) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
+  int rc = csr_keep_rows(ga, keep);
+  cudaStreamSynchronize(ga->ctx->stream);
   return rc;
 }
 

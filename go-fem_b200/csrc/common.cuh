@@ -79,6 +79,7 @@ struct femb200_assembler {
   bool own_nodes = true;
   int64_t n_nodes = 0;
   int32_t mdpn = 0;
+  const uint8_t *d_node_mask = nullptr; // optional: only rows of nodes with mask != 0 are assembled (row-block restriction)
   femb200::DeviceCsr K;
   femb200::LastPlan plan;
   int32_t err_kind = 0;
@@ -138,6 +139,11 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
                   const int32_t *conn32, int64_t n_elem, SymbolicResult *sym);
 bool numeric_supported(const ElemShape &sh);
 int csr_merge_into(femb200_assembler *ga, DeviceCsr *add); // K += add (consumes add)
+int csr_accumulate_rows(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
+                        const double *values);
+int csr_keep_rows(femb200_assembler *ga, const uint8_t *keep);
+int csr_add_entries(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
+                    const double *values);
 int csr_matvec(femb200_assembler *ga, const double *d_x, double *d_y);
 int strains_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32,
                   int64_t n_elem, const int32_t *d_dofmap, const double *d_u, double *d_strains);

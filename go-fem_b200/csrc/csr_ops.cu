@@ -85,6 +85,144 @@ int csr_merge_into(femb200_assembler *ga, DeviceCsr *add) {
   return 0;
 }
 
+// ---- multi-GPU pack / unpack ----------------------------------------------------------------------------
+__global__ void k_scatter_lens(int64_t n, const int64_t *__restrict__ rows, const int64_t *__restrict__ indptr, int64_t *__restrict__ len) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) len[rows[i]] = indptr[i + 1] - indptr[i];
+}
+
+int csr_accumulate_rows(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
+                        const double *values) {
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  if (n_rows == 0) return 0;
+  const int64_t n = ga->K.n_rows;
+  int rc;
+  DeviceCsr add;
+  add.n_rows = n;
+  int64_t *len = nullptr;
+  if ((rc = dev_alloc(ctx, &len, n + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &add.indptr, n + 1))) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(len, 0, sizeof(int64_t) * (n + 1), st));
+  k_scatter_lens<<<grid_for(n_rows, 256), 256, 0, st>>>(n_rows, rows, indptr, len);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, len, add.indptr, (int)(n + 1), st);
+  if (tb > ctx->cub_tmp_bytes) {
+    if (ctx->cub_tmp) cudaFreeAsync(ctx->cub_tmp, st);
+    ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
+    FEMB_CUDA_OK(ctx, cudaMallocAsync(&ctx->cub_tmp, tb + 256, ctx->pool, st));
+    ctx->cub_tmp_bytes = tb + 256;
+  }
+  tb = ctx->cub_tmp_bytes;
+  FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, len, add.indptr, (int)(n + 1), st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  add.nnz = ctx->h_scalars[0];
+  if ((rc = dev_alloc(ctx, &add.indices, add.nnz))) return rc;
+  if ((rc = dev_alloc(ctx, &add.values, add.nnz))) return rc;
+  // rows ascending => the packed order is already the CSR order of the embedded matrix
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(add.indices, indices, sizeof(int32_t) * add.nnz, cudaMemcpyDeviceToDevice, st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(add.values, values, sizeof(double) * add.nnz, cudaMemcpyDeviceToDevice, st));
+  ctx->launches += 3;
+  dev_free(ctx, len);
+  if (ga->K.nnz == 0 && add.nnz == 0) { dev_free(ctx, add.indptr); dev_free(ctx, add.indices); dev_free(ctx, add.values); return 0; }
+  return csr_merge_into(ga, &add);
+}
+
+// in-place add of received interface rows: warp per received row, one binary search per entry
+__global__ void k_add_entries(int64_t n_rows, const int64_t *__restrict__ rows, const int64_t *__restrict__ ptr0,
+                              const int32_t *__restrict__ idx, const double *__restrict__ val, const int64_t *__restrict__ kptr,
+                              const int32_t *__restrict__ kidx, double *__restrict__ kval, unsigned long long *err, int check_only) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_rows) return;
+  const int64_t r = rows[w];
+  const int64_t lo0 = kptr[r], hi0 = kptr[r + 1];
+  for (int64_t k = ptr0[w] + lane; k < ptr0[w + 1]; k += 32) {
+    const int32_t c = idx[k];
+    int64_t lo = lo0, hi = hi0;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (kidx[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    if (lo < hi0 && kidx[lo] == c) { if (!check_only) kval[lo] += val[k]; }   // (row, col) unique within a piece: no two lanes share a slot
+    else atomicMin(err, (unsigned long long)r);
+  }
+}
+
+int csr_add_entries(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
+                    const double *values) {
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  if (n_rows == 0) return 0;
+  if (ga->K.nnz == 0) return FEMB200_ERR_PATTERN;
+  *ctx->h_err = kNoError;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+  // pass 1 checks that every entry is in the pattern (K untouched on failure), pass 2 adds
+  k_add_entries<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(n_rows, rows, indptr, indices, values, ga->K.indptr, ga->K.indices, ga->K.values, ctx->d_err, 1);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (*ctx->h_err != kNoError) return FEMB200_ERR_PATTERN;
+  k_add_entries<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(n_rows, rows, indptr, indices, values, ga->K.indptr, ga->K.indices, ga->K.values, ctx->d_err, 0);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+__global__ void k_keep_lens(int64_t n, const int64_t *__restrict__ ptr, const uint8_t *__restrict__ keep, int64_t *__restrict__ len) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  len[r] = (r < n && keep[r]) ? ptr[r + 1] - ptr[r] : 0;
+}
+// warp per row copy
+__global__ void k_keep_copy(int64_t n, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, const double *__restrict__ val,
+                            const uint8_t *__restrict__ keep, const int64_t *__restrict__ nptr, int32_t *__restrict__ nidx, double *__restrict__ nval) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n || !keep[r]) return;
+  const int64_t s = ptr[r], d = nptr[r], m = ptr[r + 1] - s;
+  for (int64_t k = lane; k < m; k += 32) { nidx[d + k] = idx[s + k]; nval[d + k] = val[s + k]; }
+}
+
+int csr_keep_rows(femb200_assembler *ga, const uint8_t *keep) {
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  DeviceCsr &K = ga->K;
+  const int64_t n = K.n_rows;
+  if (K.nnz == 0 || n == 0) return 0;
+  int rc;
+  DeviceCsr out;
+  out.n_rows = n;
+  int64_t *len = nullptr;
+  if ((rc = dev_alloc(ctx, &len, n + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &out.indptr, n + 1))) return rc;
+  k_keep_lens<<<grid_for(n + 1, 256), 256, 0, st>>>(n, K.indptr, keep, len);
+  size_t tb = ctx->cub_tmp_bytes;
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, len, out.indptr, (int)(n + 1), st);
+  if (need > ctx->cub_tmp_bytes) {
+    if (ctx->cub_tmp) cudaFreeAsync(ctx->cub_tmp, st);
+    ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
+    FEMB_CUDA_OK(ctx, cudaMallocAsync(&ctx->cub_tmp, need + 256, ctx->pool, st));
+    ctx->cub_tmp_bytes = need + 256;
+  }
+  tb = ctx->cub_tmp_bytes;
+  FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, len, out.indptr, (int)(n + 1), st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, out.indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  out.nnz = ctx->h_scalars[0];
+  if ((rc = dev_alloc(ctx, &out.indices, out.nnz))) return rc;
+  if ((rc = dev_alloc(ctx, &out.values, out.nnz))) return rc;
+  k_keep_copy<<<grid_for(n * 32, 256), 256, 0, st>>>(n, K.indptr, K.indices, K.values, keep, out.indptr, out.indices, out.values);
+  ctx->launches += 4;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  dev_free(ctx, len);
+  dev_free(ctx, K.indptr); dev_free(ctx, K.indices); dev_free(ctx, K.values);
+  K = out;
+  return 0;
+}
+
 // warp per row, shuffle reduction (fixed lane order => deterministic)
 __global__ void k_matvec(int64_t n_rows, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                          const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y) {

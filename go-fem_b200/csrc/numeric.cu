@@ -250,6 +250,7 @@ __device__ __forceinline__ void e_b(const double (&E)[BT<BKIND, D>::NDN][BT<BKIN
 
 struct NumArgs {
   int64_t n_nodes;
+  int64_t n_numeric;          // elements [n_numeric, n_elem) are pattern-only (halo): no values
   const double *nodes;        // [n_nodes][3]
   const int32_t *conn;        // [n_elem][NN]
   const int32_t *n2e_ptr;     // [n_nodes+1]
@@ -281,6 +282,7 @@ k_numeric_rows(const NumArgs a) {
   const int beg = a.n2e_ptr[I], end = a.n2e_ptr[I + 1];
   const int64_t b0 = a.blkptr[I];
   const int rl = (int)(a.blkptr[I + 1] - b0);
+  if (rl == 0) return;                 // unreferenced node, or a row this rank does not assemble
   const int nu = SMEM_ACC ? NDN : a.nu;
   double *const vrow = a.values + (int64_t)nu * nu * b0; // this block row's slice of CSR values
 
@@ -303,6 +305,7 @@ k_numeric_rows(const NumArgs a) {
   for (int k = beg; k < end; ++k) {
     const uint32_t t = a.n2e_t[k];
     const int64_t e = t / NN;
+    if (e >= a.n_numeric) continue;
     const int la = (int)(t % NN);
     double X[NN][D];
     {
@@ -416,6 +419,7 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
 
 struct DofArgs {
   int64_t n_rows;             // n_nodes * NDN scalar rows
+  int64_t n_numeric;          // elements [n_numeric, n_elem) are pattern-only (halo): no values
   const int32_t *n2e_ptr;
   const uint32_t *n2e_t;
   const uint16_t *pos16;
@@ -481,11 +485,13 @@ k_rows_dof(const DofArgs a) {
   const int beg = a.n2e_ptr[I], end = a.n2e_ptr[I + 1];
   const int64_t b0 = a.blkptr[I];
   const int rl = (int)(a.blkptr[I + 1] - b0);
+  if (rl == 0) return;                 // unreferenced node, or a row this rank does not assemble
   const int rowsz = rl * NDN;
   for (int m = 0; m < rowsz; ++m) s_R[m * T + tid] = 0.0;
   for (int k = beg; k < end; ++k) {
     const uint32_t t = __ldg(a.n2e_t + k);
     const int64_t e = t / NN;
+    if (e >= a.n_numeric) continue;
     const int la = (int)(t % NN);
     // row-local slot positions of the element's nn nodes (the element->slot map), vector loads when aligned
     int pos[NN];
@@ -605,7 +611,7 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
     ctx->launches++;
   }
   DofArgs a;
-  a.n_rows = ga->n_nodes * B::NDN; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
+  a.n_rows = ga->n_nodes * B::NDN; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
   a.stag = stag; a.values = sym->csr.values; a.tab_g = d_tab; a.nqp = sh.nqp;
   if (a.n_rows) {
     rows<<<grid_for(a.n_rows, bestT), bestT, per_thread * bestT, ctx->stream>>>(a);
@@ -714,6 +720,7 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
   NumArgs a;
   a.n_nodes = ga->n_nodes;
+  a.n_numeric = n_elem;
   a.nodes = ga->d_nodes;
   a.conn = conn32;
   a.n2e_ptr = sym->n2e_ptr;

@@ -69,11 +69,13 @@ template <int NN>
 __global__ void __launch_bounds__(128)
 k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__restrict__ n2e_t,
               const int32_t *__restrict__ conn, int32_t *__restrict__ tmpcols, int64_t *__restrict__ rowlen,
-              uint16_t *__restrict__ pos16, int cap_s, unsigned long long *err, int only_flagged) {
+              uint16_t *__restrict__ pos16, int cap_s, unsigned long long *err, int only_flagged,
+              const uint8_t *__restrict__ node_mask) {
   extern __shared__ int32_t s_list[];
   const int T = blockDim.x, tid = threadIdx.x;
   int64_t I = (int64_t)blockIdx.x * T + tid;
   if (I >= n_nodes) return;
+  if (node_mask && !node_mask[I]) { rowlen[I] = 0; return; } // row not assembled on this rank
   if (only_flagged && rowlen[I] >= 0) return; // already done by k_row_pattern_group
   const int beg = n2e_ptr[I], end = n2e_ptr[I + 1];
   for (int a = beg + 1; a < end; ++a) { // incidence list into ascending element order (insertion sort, in place)
@@ -144,7 +146,7 @@ template <int NN, int HS>
 __global__ void __launch_bounds__(256)
 k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__restrict__ n2e_t,
                     const int32_t *__restrict__ conn, int32_t *__restrict__ tmpcols, int64_t *__restrict__ rowlen,
-                    uint16_t *__restrict__ pos16) {
+                    uint16_t *__restrict__ pos16, const uint8_t *__restrict__ node_mask) {
   constexpr int G = 8, IPL = 4, MAXINC = G * IPL;
   constexpr int CAP = HS * 3 / 4;
   constexpr int LOG = HS == 32 ? 5 : (HS == 64 ? 6 : 7);
@@ -157,6 +159,7 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   int32_t *ul = reinterpret_cast<int32_t *>(lst + MAXINC);
   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + tid) / G;
   if (I >= n_nodes) return;
+  if (node_mask && !node_mask[I]) { if (l == 0) rowlen[I] = 0; return; } // row not assembled on this rank
   const int gshift = (tid & 31) & ~(G - 1);
   const unsigned gmask = 0xffu << gshift;
   const int beg = n2e_ptr[I], end = n2e_ptr[I + 1];
@@ -326,7 +329,7 @@ __global__ void k_expand(int64_t n_nodes, int64_t nblk, int nn, int mdpn, int nu
 
 template <int NN>
 static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *n2e_ptr, uint32_t *n2e_t,
-                              const int32_t *conn, int32_t *tmpcols, int64_t *rowlen, uint16_t *pos16) {
+                              const int32_t *conn, int32_t *tmpcols, int64_t *rowlen, uint16_t *pos16, const uint8_t *node_mask) {
   const bool no_hash = getenv("FEMB200_NO_HASH_PATTERN") != nullptr;
   if (!no_hash) {
     constexpr int HS = NN <= 4 ? 32 : (NN <= 8 ? 64 : 128);
@@ -334,7 +337,7 @@ static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *
     const int T = 256;
     const size_t smem = (size_t)(T / 8) * GW * sizeof(int32_t);
     FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(k_row_pattern_group<NN, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_row_pattern_group<NN, HS><<<grid_for(n_nodes * 8, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16);
+    k_row_pattern_group<NN, HS><<<grid_for(n_nodes * 8, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, node_mask);
     ctx->launches++;
   }
   const int T = 128;
@@ -342,7 +345,7 @@ static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *
   int cap_s = NN <= 4 ? 48 : (NN <= 8 ? 64 : 96);
   size_t smem = (size_t)cap_s * T * sizeof(int32_t);
   FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(k_row_pattern<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_row_pattern<NN><<<grid_for(n_nodes, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, cap_s, ctx->d_err, no_hash ? 0 : 1);
+  k_row_pattern<NN><<<grid_for(n_nodes, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, cap_s, ctx->d_err, no_hash ? 0 : 1, node_mask);
   ctx->launches++;
   FEMB_CUDA_OK(ctx, cudaGetLastError());
   return 0;
@@ -404,11 +407,11 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn))) return rc;
   FEMB_CUDA_OK(ctx, cudaMemsetAsync(rowlen + n_nodes, 0, sizeof(int64_t), st));
   switch (nn) {
-  case 3: rc = launch_row_pattern<3>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
-  case 4: rc = launch_row_pattern<4>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
-  case 8: rc = launch_row_pattern<8>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
-  case 10: rc = launch_row_pattern<10>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
-  case 20: rc = launch_row_pattern<20>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16); break;
+  case 3: rc = launch_row_pattern<3>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
+  case 4: rc = launch_row_pattern<4>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
+  case 8: rc = launch_row_pattern<8>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
+  case 10: rc = launch_row_pattern<10>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
+  case 20: rc = launch_row_pattern<20>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
   default: rc = FEMB200_ERR_UNSUPPORTED;
   }
   if (rc) return rc;

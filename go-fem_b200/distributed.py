@@ -1,0 +1,372 @@
+"""Multi-GPU assembly: element partition in space-filling-curve order, one process per GPU, row-block
+ownership, and the exchange of interface rows (BASELINE.json north_star).
+
+    rank p:  K_p  = assemble(elements of chunk p)                   local symbolic + numeric on its GPU
+             for q != p: send the rows of K_p owned by q            pack (device gathers) -> all-to-all (NCCL / NVLink)
+             K_p  <- rows owned by p                                femb200_csr_keep_rows_device
+             K_p += piece from q, q ascending                       femb200_csr_add_entries_device (in place: the local symbolic
+                                                                    phase listed the halo elements, so owned rows already have
+                                                                    their final pattern) or ..._accumulate_rows_device (union);
+                                                                    fixed order => bit-reproducible run to run
+    => every rank owns a row block of the distributed CSR K, in the caller's global DOF numbering.
+
+Row ownership: a node belongs to the lowest rank that has an element touching it (unreferenced nodes to rank
+0), so with a space-filling-curve element order only the partition surfaces are exchanged.
+
+The host-side logic here (partition, ownership, send lists, the all-to-all of ragged CSR pieces) is backend
+agnostic: tests run it on CPU with gloo and world_size 2; on the B200 box the same code moves device tensors
+over NCCL.  Local assembly and the two device-side pack/unpack steps are injected (`LocalBackend`).
+"""
+import numpy as np
+
+
+# ----------------------------------------------------------------------------- partition (host, once per mesh)
+def morton_order(nodes, conn, bits=21):
+    """Element permutation by the Morton (Z-order) key of the element centroid, 21 bits per axis."""
+    c = nodes[conn].mean(axis=1)
+    lo, hi = c.min(axis=0), c.max(axis=0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((c - lo) / span * (2 ** bits - 1)).astype(np.uint64), np.uint64(2 ** bits - 1))
+
+    def spread(v):
+        v = v & np.uint64(0x1FFFFF)
+        v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+        return v
+
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+    return np.argsort(key, kind="stable")
+
+
+def chunk_bounds(n_elem, world):
+    """Contiguous chunks of (almost) equal element count."""
+    return [(n_elem * r) // world for r in range(world + 1)]
+
+
+def node_owner(n_nodes, conn, bounds):
+    """owner[node] = lowest rank with an element touching the node (rank 0 for unreferenced nodes)."""
+    world = len(bounds) - 1
+    owner = np.full(n_nodes, world, dtype=np.int32)
+    for r in range(world - 1, -1, -1):          # descending: the lowest rank writes last
+        touched = np.unique(conn[bounds[r]:bounds[r + 1]])
+        owner[touched] = r
+    owner[owner == world] = 0
+    return owner
+
+
+class ExchangePlan:
+    """What rank `rank` sends: for every other rank q the ascending scalar rows (global ids) of nodes that
+    this rank's elements touch and q owns; plus the keep mask of its own row block."""
+
+    def __init__(self, n_nodes, conn, bounds, rank, mdpn, owner=None):
+        world = len(bounds) - 1
+        self.world, self.rank, self.mdpn = world, rank, mdpn
+        self.owner = node_owner(n_nodes, conn, bounds) if owner is None else owner
+        touched = np.unique(conn[bounds[rank]:bounds[rank + 1]])
+        self.send_rows = []
+        for q in range(world):
+            if q == rank:
+                self.send_rows.append(np.zeros(0, dtype=np.int64))
+                continue
+            nd = touched[self.owner[touched] == q].astype(np.int64)
+            rows = (nd[:, None] * mdpn + np.arange(mdpn, dtype=np.int64)[None, :]).ravel()
+            self.send_rows.append(rows)
+        self.keep_mask = np.repeat(self.owner == rank, mdpn).astype(np.uint8)
+        self.owned_rows = np.nonzero(self.keep_mask)[0].astype(np.int64)
+        # halo: elements of other chunks that touch a node this rank owns.  Listed as pattern-only elements in the
+        # local symbolic phase, they give the owned rows their FINAL pattern, so incoming interface values are
+        # added in place (no pattern union, no reallocation).
+        mine = self.owner == rank
+        self.own_node_mask = mine.astype(np.uint8)
+        own_conn = conn[bounds[rank]:bounds[rank + 1]]
+        foreign = ~mine
+        self.send_node_mask = np.zeros(n_nodes, dtype=np.uint8)
+        self.send_node_mask[touched[foreign[touched]]] = 1
+        # own elements that touch a node owned by someone else: the only ones that produce interface rows
+        self.send_elems = np.nonzero(foreign[own_conn].any(axis=1))[0]
+        other = np.ones(conn.shape[0], dtype=bool)
+        other[bounds[rank]:bounds[rank + 1]] = False
+        self.halo_elems = np.nonzero(other & mine[conn].any(axis=1))[0]
+
+    def local_connectivity(self, conn, bounds):
+        """(connectivity to hand to the local assembler, number of trailing pattern-only elements)"""
+        own = conn[bounds[self.rank]:bounds[self.rank + 1]]
+        if self.halo_elems.size == 0:
+            return own, 0
+        return np.concatenate([own, conn[self.halo_elems]], axis=0), int(self.halo_elems.size)
+
+
+# ----------------------------------------------------------------------------- ragged CSR pieces (torch tensors)
+def gather_rows(indptr, indices, values, rows):
+    """Packs the given (ascending) rows of a CSR held in torch tensors: returns (lens, indices, values)."""
+    import torch
+    if rows.numel() == 0:
+        return rows.new_zeros(0), indices.new_zeros(0), values.new_zeros(0)
+    start = indptr[rows]
+    lens = indptr[rows + 1] - start
+    total = int(lens.sum().item())
+    if total == 0:
+        return lens, indices.new_zeros(0), values.new_zeros(0)
+    off = torch.cumsum(lens, 0) - lens
+    gidx = torch.repeat_interleave(start - off, lens) + torch.arange(total, device=rows.device, dtype=rows.dtype)
+    return lens, indices[gidx], values[gidx]
+
+
+def all_to_all_ragged(pieces, world, rank, device, dist):
+    """pieces[q] = (rows int64, lens int64, indices int32, values f64) to send to q.  Returns the pieces
+    received from every rank, same tuple layout.  Two collectives: the sizes, then ONE byte payload per peer
+    ([rows | lens | values | indices], 8-byte fields first) -- the interface is small, so latency dominates."""
+    import torch
+    sizes = torch.tensor([[p[0].numel(), p[2].numel()] for p in pieces], dtype=torch.int64, device=device)
+    rsizes = torch.empty_like(sizes)
+    dist.all_to_all_single(rsizes, sizes)
+    rs = rsizes.cpu().numpy()
+    ss = sizes.cpu().numpy()
+
+    def nbytes(a):
+        return int(a[0]) * 16 + int(a[1]) * 12
+
+    def as_bytes(t):
+        if t.numel() == 0:
+            return torch.empty(0, dtype=torch.uint8, device=device)
+        return t.contiguous().view(torch.uint8)
+
+    send = torch.cat([torch.cat([as_bytes(p[0].to(torch.int64)), as_bytes(p[1].to(torch.int64)), as_bytes(p[3].to(torch.float64)),
+                                 as_bytes(p[2].to(torch.int32))]) for p in pieces])
+    recv = torch.empty(sum(nbytes(r) for r in rs), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv, send, output_split_sizes=[nbytes(r) for r in rs], input_split_sizes=[nbytes(x) for x in ss])
+    out, off = [], 0
+    for q in range(world):
+        nr, nz = int(rs[q, 0]), int(rs[q, 1])
+        rows = recv[off:off + 8 * nr].view(torch.int64); off += 8 * nr
+        lens = recv[off:off + 8 * nr].view(torch.int64); off += 8 * nr
+        val = recv[off:off + 8 * nz].view(torch.float64); off += 8 * nz
+        idx = recv[off:off + 4 * nz].view(torch.int32); off += 4 * nz
+        out.append((rows, lens, idx, val))
+    return out
+
+
+class LocalBackend:
+    """Injected per-rank operations.  csr_tensors() -> (indptr, indices, values) torch views of the local K;
+    keep_rows(mask_tensor); accumulate_rows(rows, indptr0, indices, values)."""
+
+    def csr_tensors(self):
+        raise NotImplementedError
+
+    def keep_rows(self, mask):
+        raise NotImplementedError
+
+    def accumulate_rows(self, rows, indptr0, indices, values):
+        raise NotImplementedError
+
+    def add_entries(self, rows, indptr0, indices, values):
+        """In-place add when the pattern already holds every entry; returns False when it does not."""
+        return False
+
+
+def exchange_and_own(backend, plan, device, dist, timings=None):
+    """The collective step: after local assembly, leaves `backend` holding exactly the rank's row block.
+    timings: optional dict filled with host-clock milliseconds per sub-step (synchronising; diagnostics only)."""
+    import time
+    import torch
+
+    def mark(name, t0):
+        if timings is not None:
+            if device.type == "cuda":
+                torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+        return time.perf_counter()
+
+    t0 = time.perf_counter()
+    indptr, indices, values = backend.csr_tensors()
+    pieces = []
+    for q in range(plan.world):
+        rows = torch.as_tensor(plan.send_rows[q], device=device)
+        lens, idx, val = gather_rows(indptr, indices, values, rows)
+        pieces.append((rows, lens, idx, val))
+    t0 = mark("pack", t0)
+    received = all_to_all_ragged(pieces, plan.world, plan.rank, device, dist)
+    t0 = mark("all_to_all", t0)
+    backend.keep_rows(torch.as_tensor(plan.keep_mask, device=device))
+    t0 = mark("keep_rows", t0)
+    for q in range(plan.world):                      # fixed order: ascending source rank
+        if q == plan.rank:
+            continue
+        rows, lens, idx, val = received[q]
+        if rows.numel() == 0:
+            continue
+        ptr0 = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=device)
+        torch.cumsum(lens, 0, out=ptr0[1:])
+        if not backend.add_entries(rows, ptr0, idx, val):     # owned rows carry their halo pattern: in place
+            backend.accumulate_rows(rows, ptr0, idx, val)     # generic path: pattern union
+    mark("accumulate", t0)
+    return sum(int(p[3].numel()) * 12 + int(p[0].numel()) * 16 for p in pieces)   # bytes sent (values+indices, rows+lens)
+
+
+def exchange_into_owned(owned, outgoing, plan, device, dist, timings=None):
+    """Optimised collective step (what bench.py times).  `owned` was assembled with the node mask of the rank's
+    row block over [own elements ; halo elements (pattern only)], so it IS the row block with its final pattern
+    and the rank's own contributions; `outgoing` was assembled with the mask of the foreign nodes over the own
+    elements that touch them, so it holds exactly the interface rows to send.  Nothing is computed and then
+    dropped, and the received values are added in place in ascending source-rank order."""
+    import time
+    import torch
+
+    def mark(name, t0):
+        if timings is not None:
+            if device.type == "cuda":
+                torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+        return time.perf_counter()
+
+    t0 = time.perf_counter()
+    indptr, indices, values = outgoing.csr_tensors()
+    pieces = []
+    for q in range(plan.world):
+        rows = torch.as_tensor(plan.send_rows[q], device=device)
+        lens, idx, val = gather_rows(indptr, indices, values, rows)
+        pieces.append((rows, lens, idx, val))
+    t0 = mark("pack", t0)
+    received = all_to_all_ragged(pieces, plan.world, plan.rank, device, dist)
+    t0 = mark("all_to_all", t0)
+    for q in range(plan.world):                      # fixed order: ascending source rank
+        if q == plan.rank:
+            continue
+        rows, lens, idx, val = received[q]
+        if rows.numel() == 0:
+            continue
+        ptr0 = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=device)
+        torch.cumsum(lens, 0, out=ptr0[1:])
+        if not owned.add_entries(rows, ptr0, idx, val):
+            owned.accumulate_rows(rows, ptr0, idx, val)
+    mark("accumulate", t0)
+    return sum(int(p[3].numel()) * 12 + int(p[0].numel()) * 16 for p in pieces)
+
+
+# ----------------------------------------------------------------------------- backends
+class DeviceView:
+    """Zero-copy torch view of library-owned device memory (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, n, typestr, device):
+    import torch
+    if n == 0 or not ptr:
+        dt = {"<i8": torch.int64, "<i4": torch.int32, "<f8": torch.float64}[typestr]
+        return torch.empty(0, dtype=dt, device=device)
+    return torch.as_tensor(DeviceView(ptr, n, typestr), device=device)
+
+
+class Femb200Backend(LocalBackend):
+    """The GPU library as the local backend (RawAssembler from the package)."""
+
+    def __init__(self, pkg, raw, device):
+        import ctypes
+        self.pkg, self.raw, self.device, self.C = pkg, raw, device, ctypes
+
+    def csr_tensors(self):
+        ip, ix, va = self.raw.csr_device()
+        n, nnz = self.raw.total_dofs(), self.raw.nnz()
+        return (device_tensor(ip, n + 1, "<i8", self.device), device_tensor(ix, nnz, "<i4", self.device),
+                device_tensor(va, nnz, "<f8", self.device))
+
+    def keep_rows(self, mask):
+        rc = self.pkg.lib().femb200_csr_keep_rows_device(self.raw.h, self.C.c_void_p(mask.data_ptr()))
+        if rc:
+            raise RuntimeError(f"femb200_csr_keep_rows_device -> {rc}")
+
+    def accumulate_rows(self, rows, indptr0, indices, values):
+        c = self.C.c_void_p
+        rc = self.pkg.lib().femb200_csr_accumulate_rows_device(self.raw.h, rows.numel(), c(rows.data_ptr()), c(indptr0.data_ptr()),
+                                                                c(indices.data_ptr()), c(values.data_ptr()))
+        if rc:
+            raise RuntimeError(f"femb200_csr_accumulate_rows_device -> {rc}")
+
+
+    def add_entries(self, rows, indptr0, indices, values):
+        c = self.C.c_void_p
+        rc = self.pkg.lib().femb200_csr_add_entries_device(self.raw.h, rows.numel(), c(rows.data_ptr()), c(indptr0.data_ptr()),
+                                                            c(indices.data_ptr()), c(values.data_ptr()))
+        if rc not in (0, 24):
+            raise RuntimeError(f"femb200_csr_add_entries_device -> {rc}")
+        return rc == 0
+
+
+class NumpyBackend(LocalBackend):
+    """CPU stand-in used by the gloo tests: holds a canonical CSR in numpy, merges like the device kernels
+    (pattern union, explicit zeros kept, existing value + piece)."""
+
+    def __init__(self, indptr, indices, values):
+        self.indptr, self.indices, self.values = indptr.copy(), indices.copy(), values.copy()
+
+    def csr_tensors(self):
+        import torch
+        return torch.from_numpy(self.indptr), torch.from_numpy(self.indices), torch.from_numpy(self.values)
+
+    def keep_rows(self, mask):
+        keep = mask.numpy().astype(bool)
+        lens = np.diff(self.indptr) * keep
+        rowid = np.repeat(np.arange(lens.size), np.diff(self.indptr))
+        sel = keep[rowid]
+        self.indices, self.values = self.indices[sel], self.values[sel]
+        self.indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+
+    def add_entries(self, rows, indptr0, indices, values):
+        rows, ptr, idx, val = rows.numpy(), indptr0.numpy(), indices.numpy(), values.numpy()
+        slots = np.empty(idx.size, dtype=np.int64)
+        for w, r in enumerate(rows):
+            lo, hi = self.indptr[r], self.indptr[r + 1]
+            seg = idx[ptr[w]:ptr[w + 1]]
+            pos = lo + np.searchsorted(self.indices[lo:hi], seg)
+            if np.any(pos >= hi) or np.any(self.indices[np.minimum(pos, hi - 1)] != seg):
+                return False
+            slots[ptr[w]:ptr[w + 1]] = pos
+        self.values[slots] += val
+        return True
+
+    def accumulate_rows(self, rows, indptr0, indices, values):
+        rows, ptr, idx, val = rows.numpy(), indptr0.numpy(), indices.numpy(), values.numpy()
+        n = self.indptr.size - 1
+        a_row = np.repeat(np.arange(n), np.diff(self.indptr))
+        b_row = np.repeat(rows, np.diff(ptr))
+        r = np.concatenate([a_row, b_row])
+        c = np.concatenate([self.indices, idx]).astype(np.int64)
+        v = np.concatenate([self.values, val])
+        order = np.lexsort((np.arange(r.size), c, r))            # stable: existing entry before the piece
+        r, c, v = r[order], c[order], v[order]
+        first = np.ones(r.size, dtype=bool)
+        first[1:] = (r[1:] != r[:-1]) | (c[1:] != c[:-1])
+        starts = np.nonzero(first)[0]
+        self.values = np.add.reduceat(v, starts) if r.size else v
+        self.indices = c[starts].astype(np.int32)
+        self.indptr = np.concatenate([[0], np.cumsum(np.bincount(r[starts], minlength=n))]).astype(np.int64)
+
+
+def gather_distributed_csr(backend, plan, dist, device):
+    """Test helper: collects every rank's row block on every rank -> the full canonical CSR (host numpy)."""
+    import torch
+    indptr, indices, values = backend.csr_tensors()
+    lens = (indptr[1:] - indptr[:-1]).cpu()
+    world = plan.world
+    objs = [None] * world
+    dist.all_gather_object(objs, (lens.numpy(), indices.cpu().numpy(), values.cpu().numpy()))
+    n = lens.numel()
+    total_lens = np.zeros(n, dtype=np.int64)
+    for ln, _, _ in objs:
+        assert not np.any((total_lens > 0) & (ln > 0)), "two ranks own the same row"
+        total_lens += ln
+    ptr = np.concatenate([[0], np.cumsum(total_lens)]).astype(np.int64)
+    idx = np.zeros(ptr[-1], dtype=np.int32)
+    val = np.zeros(ptr[-1])
+    for ln, ix, va in objs:
+        rows = np.nonzero(ln)[0]
+        src = np.concatenate([[0], np.cumsum(ln[rows])])
+        for k, r in enumerate(rows):
+            idx[ptr[r]:ptr[r + 1]] = ix[src[k]:src[k + 1]]
+            val[ptr[r]:ptr[r + 1]] = va[src[k]:src[k + 1]]
+    return ptr, idx, val

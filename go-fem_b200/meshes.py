@@ -38,42 +38,46 @@ def jitter(nodes, interior_mask, h, amp=0.15, axes=3):
 # ----------------------------------------------------------------------------- Tetra4 (BCC cube)
 def bcc_tetra4(N, box=1.0, jittered=True):
     """BCC tetra mesh of [0,box]^3 with N cells per side: 12*N^2*(N-1) tets, (N+1)^3+N^3 nodes."""
-    h = box / N
-    M = N + 1
-    g = np.arange(M, dtype=np.float64) * h
-    cx, cy, cz = np.meshgrid(g, g, g, indexing="ij")
-    corners = np.stack([cx.ravel(), cy.ravel(), cz.ravel()], axis=1)
-    c = (np.arange(N, dtype=np.float64) + 0.5) * h
-    mx, my, mz = np.meshgrid(c, c, c, indexing="ij")
-    centres = np.stack([mx.ravel(), my.ravel(), mz.ravel()], axis=1)
+    return bcc_tetra4_box(N, N, N, box / N, jittered)
+
+
+def bcc_tetra4_box(nx, ny, nz, h=1.0, jittered=True):
+    """BCC tetra mesh of an nx x ny x nz cell box (cell size h): corner nodes (x-major) then cell centres;
+    4 tets (centre-, centre+, face edge k) per interior cell face, elements in cell-major order."""
+    Mx, My, Mz = nx + 1, ny + 1, nz + 1
+    cx, cy, cz = np.meshgrid(np.arange(Mx) * h, np.arange(My) * h, np.arange(Mz) * h, indexing="ij")
+    corners = np.stack([cx.ravel(), cy.ravel(), cz.ravel()], axis=1).astype(np.float64)
+    mx, my, mz = np.meshgrid((np.arange(nx) + 0.5) * h, (np.arange(ny) + 0.5) * h, (np.arange(nz) + 0.5) * h, indexing="ij")
+    centres = np.stack([mx.ravel(), my.ravel(), mz.ravel()], axis=1).astype(np.float64)
     nodes = np.concatenate([corners, centres], axis=0)
-    ncorner = M ** 3
+    ncorner = Mx * My * Mz
 
     def cid(i, j, k):
-        return (i * M + j) * M + k
+        return (i * My + j) * Mz + k
 
     def mid(i, j, k):
-        return ncorner + (i * N + j) * N + k
+        return ncorner + (i * ny + j) * nz + k
 
     tets, keys = [], []
+    dims = (nx, ny, nz)
     for axis in range(3):
-        # interior faces orthogonal to `axis`, between cell (.., a-1, ..) and cell (.., a, ..), a = 1..N-1
-        a = np.arange(1, N)
-        b = np.arange(N)
-        A, B, Cc = np.meshgrid(a, b, b, indexing="ij")
+        # interior faces orthogonal to `axis`, between cell a-1 and cell a along it, a = 1..n_axis-1
+        o1, o2 = [d for d in range(3) if d != axis]
+        a = np.arange(1, dims[axis])
+        A, B, Cc = np.meshgrid(a, np.arange(dims[o1]), np.arange(dims[o2]), indexing="ij")
         A, B, Cc = A.ravel(), B.ravel(), Cc.ravel()
         if axis == 0:
             lo, hi = mid(A - 1, B, Cc), mid(A, B, Cc)
             f = [cid(A, B, Cc), cid(A, B + 1, Cc), cid(A, B + 1, Cc + 1), cid(A, B, Cc + 1)]
-            cell = ((A - 1) * N + B) * N + Cc
+            cell = ((A - 1) * ny + B) * nz + Cc
         elif axis == 1:
             lo, hi = mid(B, A - 1, Cc), mid(B, A, Cc)
             f = [cid(B, A, Cc), cid(B, A, Cc + 1), cid(B + 1, A, Cc + 1), cid(B + 1, A, Cc)]
-            cell = (B * N + (A - 1)) * N + Cc
+            cell = (B * ny + (A - 1)) * nz + Cc
         else:
             lo, hi = mid(B, Cc, A - 1), mid(B, Cc, A)
             f = [cid(B, Cc, A), cid(B + 1, Cc, A), cid(B + 1, Cc + 1, A), cid(B, Cc + 1, A)]
-            cell = (B * N + Cc) * N + (A - 1)
+            cell = (B * ny + Cc) * nz + (A - 1)
         for k in range(4):
             tets.append(np.stack([lo, hi, f[k], f[(k + 1) % 4]], axis=1))
             keys.append(cell * 12 + axis * 4 + k)
@@ -81,7 +85,8 @@ def bcc_tetra4(N, box=1.0, jittered=True):
     order = np.argsort(np.concatenate(keys), kind="stable")       # cell-major element order (locality)
     conn = conn[order]
     if jittered:
-        interior = np.all((nodes > 1e-12) & (nodes < box - 1e-12), axis=1)
+        ext = np.array([nx, ny, nz]) * h
+        interior = np.all((nodes > 1e-12) & (nodes < ext - 1e-12), axis=1)
         nodes = jitter(nodes, interior, h)
     conn = orient_tets(nodes, conn)
     return nodes, conn

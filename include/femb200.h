@@ -44,7 +44,8 @@ enum femb200_status {
   FEMB200_ERR_BAD_ARG = 20,     /* malformed descriptor (nil pointers, sizes out of range) */
   FEMB200_ERR_UNSUPPORTED = 21, /* (d, nn, ndn, dimC, bkind) combination with no compiled kernel */
   FEMB200_ERR_CUDA = 22,        /* CUDA runtime failure; text via femb200_last_cuda_error */
-  FEMB200_ERR_TOO_LARGE = 23    /* index width exceeded (row with > 65535 node blocks, nnz/row > 2^31) */
+  FEMB200_ERR_TOO_LARGE = 23,   /* index width exceeded (row with > 65535 node blocks, nnz/row > 2^31) */
+  FEMB200_ERR_PATTERN = 24      /* femb200_csr_add_entries_device: an entry is not in the pattern of K */
 };
 
 /* Everything AddIsoparametric evaluates ONCE per call on the host (assembler_isoparametric.go:29-71)
@@ -98,6 +99,14 @@ int femb200_add_isoparametric(femb200_assembler *ga, const femb200_elem_desc *de
                               const void *conn, int32_t conn_is_int64, int32_t conn_on_device,
                               int64_t n_elem);
 
+/* The same with a halo: the LAST n_pattern_only elements of conn take part in the symbolic phase only (their
+ * node pairs enter the CSR pattern with value 0) and contribute no values; they are not validated geometrically.
+ * Multi-GPU: a rank lists the neighbouring ranks' elements that touch its rows, so that the rows it owns have
+ * their final pattern before the interface values arrive. */
+int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_desc *desc,
+                                   const void *conn, int32_t conn_is_int64, int32_t conn_on_device,
+                                   int64_t n_elem, int64_t n_pattern_only);
+
 /* After a non-zero status: which error, the lowest failing element index and its first failing
  * quadrature point (-1 when not applicable). */
 int femb200_last_error(const femb200_assembler *ga, int32_t *kind, int64_t *elem, int32_t *qp);
@@ -116,6 +125,26 @@ int femb200_csr_device(const femb200_assembler *ga, const int64_t **indptr, cons
 int femb200_csr_at(const femb200_assembler *ga, int64_t i, int64_t j, double *out);
 /* K*x on the device, x and y on the host (forces.MulVec(K,u), patch_test.go:92). */
 int femb200_csr_matvec(const femb200_assembler *ga, const double *x, double *y);
+
+/* ---- multi-GPU row-block exchange (one process per GPU; the collective itself is NCCL all-to-all driven by
+ * the host layer, these are the device-side pack/unpack steps either side of it) -------------------------
+ * K += A, A given on the device as n_rows scattered rows: rows[n_rows] ascending global row ids,
+ * indptr[n_rows+1] with indptr[0] == 0, indices / values packed row after row.  Pattern union, values
+ * added after the existing ones (fixed order: the caller feeds pieces in ascending source rank). */
+int femb200_csr_accumulate_rows_device(femb200_assembler *ga, int64_t n_rows, const int64_t *rows,
+                                       const int64_t *indptr, const int32_t *indices, const double *values);
+/* Row-block restriction: from now on only the rows of nodes with node_mask[node] != 0 (device bytes, one per node,
+ * NULL = all) are assembled; the other rows stay empty.  A rank assembles its owned row block with one assembler
+ * and the interface rows it must send with another one, so no row is computed and then thrown away. */
+int femb200_assembler_set_node_mask_device(femb200_assembler *ga, const uint8_t *node_mask);
+/* K[rows] += A in place: like femb200_csr_accumulate_rows_device but every (row, column) of A must already be
+ * in the pattern of K (true for owned rows assembled with their halo).  No allocation, no pattern change;
+ * FEMB200_ERR_PATTERN if an entry is missing (checked in a first pass: K is untouched on failure). */
+int femb200_csr_add_entries_device(femb200_assembler *ga, int64_t n_rows, const int64_t *rows,
+                                   const int64_t *indptr, const int32_t *indices, const double *values);
+/* Drops every row whose keep[row] == 0 (device byte mask, one per scalar row): after sending the rows it
+ * does not own, a rank keeps exactly its row block of the distributed K. */
+int femb200_csr_keep_rows_device(femb200_assembler *ga, const uint8_t *keep);
 
 /* Element -> CSR slot map of the last add call (north_star subsystem 1):
  * slot[e][a][b] = index into the node-block CSR of block (node a of e, node b of e); the scalar entry

@@ -152,9 +152,12 @@ class GeneralAssembler:
         self._h = lib().femo_new_general_assembler(_d(nodes), self.n_nodes, int(model_dofs))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().femo_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().femo_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def total_dofs(self):
         return lib().femo_total_dofs(self._h)
