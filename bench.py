@@ -52,20 +52,63 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md clocks line).  The timed
+    region is tens of milliseconds, so NVML is polled in-process (~1 ms per sample); nvidia-smi -lms is the
+    fallback when the NVML binding is unavailable."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.gpu, self.sm, self.mx, self.reasons, self.stop_flag = gpu_index, [], [], set(), False
         self.proc = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except Exception:
+                    idx = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
 
     def run(self):
+        if self.nvml is not None:
+            while not self.stop_flag:
+                try:
+                    self._sample_nvml()
+                except Exception:
+                    break
+                time.sleep(0.001)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                r = [x.strip() for x in line.split(",")]
+                if len(r) >= 6 and r[0].replace(".", "").isdigit():
+                    self.sm.append(float(r[0]))
+                    self.mx.append(float(r[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
                 if self.stop_flag:
                     break
         except Exception:
@@ -78,16 +121,10 @@ class ClockSampler(threading.Thread):
                 self.proc.terminate()
             except Exception:
                 pass
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 6:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=2.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml polled in-process during the timed region" if self.nvml is not None else "nvidia-smi -lms 20"}
 
 
 def make_workload(name, size):
@@ -105,11 +142,21 @@ def make_workload(name, size):
 
 
 def algorithmic_bytes(w, nnz):
-    """Per-launch algorithmic bytes of the dominant kernel (numeric phase + row reduction), DESIGN.md 'Roofline':
-    int32 connectivity + node coordinates + incidence list (n2e_t) + element->slot map (pos16) read,
-    CSR values written."""
+    """Per-launch algorithmic bytes of the dominant kernel k_rows: staged geometry records
+    (one per element and quadrature point) + incidence list (n2e_t) + element->slot map (pos16) read, CSR values
+    written.  Record = 4 doubles per node when a node carries 3 values (f rides in the 4th), else nn*NV + f padded even."""
     ne, nn = w["conn"].shape
-    return 4 * nn * ne + 24 * w["nodes"].shape[0] + 4 * nn * ne + 2 * nn * nn * ne + 8 * nnz
+    nv = {"tetra4": 3, "hexa8": 3, "tetra10": 3, "hexa20": 3, "quad4": 3}[w["name"]]
+    nqp = len(w["elemT"].Quadrature()[1])
+    rec = 4 * nn if nv == 3 else ((nn * nv + 2) & ~1)
+    return 8 * rec * nqp * ne + 4 * nn * ne + 2 * nn * nn * ne + 8 * nnz
+
+
+def compulsory_bytes(w, nnz, ndof):
+    """SURVEY section 8(d) B_alg of one full call: int32 connectivity + node coordinates in, CSR (indptr int64 + indices int32 +
+    values f64) out."""
+    ne, nn = w["conn"].shape
+    return 4 * nn * ne + 24 * w["nodes"].shape[0] + 8 * (ndof + 1) + 12 * nnz
 
 
 def cpu_port_seconds(w, nodes, conn):
@@ -291,7 +338,7 @@ def _csr_dev(L, h):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="tetra4", choices=sorted(WORKLOADS))
@@ -419,15 +466,25 @@ def main():
     d2h = h_indptr.numel() * 8 + h_indices.numel() * 4 + h_values.numel() * 8
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    # k_rows (B^T C B products fused with the deterministic row reduction) has the largest share of the step.
+    # achieved = algorithmic bytes of one launch / its CUDA-event time ([9] of femb200_phase_ms: events recorded
+    # on the library's stream right before and after the launch), averaged over the timed steps.
     peak, peak_src = measured_peaks()
-    kern_ms = float(ph_mean[4])
+    names = list(pkg.TIMER_NAMES)
+    kern_ms = float(ph_mean[names.index("k_rows")])
     abytes = algorithmic_bytes(w, nnz)
     achieved = abytes / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_numeric_rows (numeric phase fused with the deterministic row reduction)",
+    probe = (C.c_double * 2)()
+    rc = L.femb200_probe_peaks(ctx_holder.ctx, 5, probe)
+    roofline = {"bound": "hbm", "kernel": "k_rows (B^T C B per scalar CSR row fused with the deterministic segmented reduction)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes": abytes, "kernel_ms": kern_ms,
-                "kernel_share_of_step": kern_ms / dev_ms}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_numeric_rows.json")
+                "kernel_share_of_step": kern_ms / dev_ms,
+                "algorithmic_bytes_def": "staged geometry records read + incidence list + element->slot map (pos16) read + CSR values written",
+                "probe_this_run": {"fp64_dfma_tflops": float(probe[0]), "hbm_copy_gbs": float(probe[1])} if rc == 0 else None,
+                "whole_step": {"compulsory_bytes": compulsory_bytes(w, nnz, ndof), "hbm_floor_ms": compulsory_bytes(w, nnz, ndof) / (peak * 1e9) * 1e3,
+                               "frac_of_hbm_roofline": compulsory_bytes(w, nnz, ndof) / (peak * 1e9) * 1e3 / dev_ms}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_k_rows.json")
     if os.path.exists(traffic_file):
         roofline["traffic"] = json.load(open(traffic_file)).get(args.config)
 

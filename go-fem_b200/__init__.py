@@ -20,8 +20,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfemb200.so")
 
-N_TIMERS = 8
-TIMER_NAMES = ["upload_validate", "adjacency", "row_pattern", "csr_expand", "numeric_rows", "merge", "total_device", "launches"]
+N_TIMERS = 10
+TIMER_NAMES = ["upload_validate", "adjacency", "row_pattern", "csr_expand", "numeric_rows", "merge", "total_device", "launches", "k_geometry", "k_rows"]
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
@@ -78,6 +78,7 @@ def lib():
     L.femb200_kernel_launches.argtypes = [vp]
     L.femb200_kernel_launches.restype = C.c_int64
     L.femb200_sync.argtypes = [vp]
+    L.femb200_probe_peaks.argtypes = [vp, C.c_int32, _dp]
     # host mirror
     L.gofem_elem_info.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _dp, _i32p, _dp, _dp, C.c_char_p, C.c_int]
     L.gofem_elem_basis.argtypes = [C.c_int, _dp, _dp, _dp, _i32p]

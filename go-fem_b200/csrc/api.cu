@@ -202,6 +202,7 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   int rc = prepare(ga, desc, &sh, &blob);
   if (rc) { ga->err_kind = rc; return rc; }
   for (float &f : ga->phase_ms) f = 0.f;
+  ga->split_numeric = false;
   const int64_t launches0 = ctx->launches;
 
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
@@ -259,6 +260,10 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
     if (cudaEventElapsedTime(&ms, ctx->ev[pairs[i][0]], ctx->ev[pairs[i][1]]) == cudaSuccess) ga->phase_ms[i] = ms;
   if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]) == cudaSuccess) ga->phase_ms[6] = ms;
   ga->phase_ms[7] = (float)(ctx->launches - launches0);
+  if (ga->split_numeric) {
+    if (cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]) == cudaSuccess) ga->phase_ms[8] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ga->phase_ms[9] = ms;
+  }
   return 0;
 }
 
@@ -430,6 +435,12 @@ int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc
   cudaStreamSynchronize(st);
   if (rc) ga->err_kind = rc;
   return rc;
+}
+
+int femb200_probe_peaks(femb200_ctx *ctx, int32_t reps, double out[2]) {
+  if (!ctx || !out) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return probe_peaks(ctx, reps, out);
 }
 
 int femb200_phase_ms(const femb200_assembler *ga, float out[FEMB200_N_TIMERS]) {

@@ -70,7 +70,7 @@ struct femb200_ctx {
   int64_t *d_scalars = nullptr;             // small device scratch (8 x int64)
   int64_t *h_scalars = nullptr;             // pinned host mirror
   unsigned long long *h_err = nullptr;      // pinned
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[12] = {};
 };
 
 struct femb200_assembler {
@@ -86,6 +86,7 @@ struct femb200_assembler {
   int64_t err_elem = -1;
   int32_t err_qp = -1;
   float phase_ms[FEMB200_N_TIMERS] = {};
+  bool split_numeric = false; // ev[9..11] bracket k_geometry / k_rows of the last call
 };
 
 namespace femb200 {
@@ -150,5 +151,6 @@ int strains_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
 int narrow_and_validate_conn(femb200_assembler *ga, const void *d_conn_in, bool is64, int64_t n, int nn,
                              int32_t *conn32_out);
 int slot_map(femb200_assembler *ga, int64_t *d_slot);
+int probe_peaks(femb200_ctx *ctx, int reps, double out[2]);
 
 } // namespace femb200

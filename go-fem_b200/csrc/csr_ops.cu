@@ -250,4 +250,58 @@ int csr_matvec(femb200_assembler *ga, const double *d_x, double *d_y) {
   return 0;
 }
 
+
+// ---- roofline probes (bench.py): FP64 vector peak and HBM copy bandwidth ----------------------------
+__global__ void __launch_bounds__(256) k_probe_dfma(double *out, int iters, double seed) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed + i + threadIdx.x;
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s; // never true: keeps the chains alive
+}
+
+__global__ void __launch_bounds__(256) k_probe_copy(const double4 *__restrict__ in, double4 *__restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+int probe_peaks(femb200_ctx *ctx, int reps, double out[2]) {
+  cudaStream_t st = ctx->stream;
+  if (reps < 1) reps = 1;
+  double *buf = nullptr;
+  const size_t n_d = (size_t)1 << 27; // 2 x 512 MiB halves
+  int rc = dev_alloc(ctx, &buf, n_d);
+  if (rc) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(buf, 0, n_d * sizeof(double), st));
+  const int iters = 4096, blocks = ctx->sm_count * 8;
+  float best_f = 1e30f, best_c = 1e30f, ms = 0;
+  for (int r = 0; r < reps + 1; ++r) {
+    FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[7], st));
+    k_probe_dfma<<<blocks, 256, 0, st>>>(buf, iters, 1.0);
+    FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[8], st));
+    FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    FEMB_CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]));
+    if (r && ms < best_f) best_f = ms;
+    FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[7], st));
+    k_probe_copy<<<ctx->sm_count * 16, 256, 0, st>>>((const double4 *)buf, (double4 *)(buf + n_d / 2), (int64_t)(n_d / 8));
+    FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[8], st));
+    FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    FEMB_CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]));
+    if (r && ms < best_c) best_c = ms;
+  }
+  ctx->launches += 2 * (reps + 1);
+  out[0] = 2.0 * 64.0 * iters * (double)blocks * 256.0 / (best_f * 1e-3) / 1e12;
+  out[1] = (double)(n_d * sizeof(double)) / (best_c * 1e-3) / 1e9; // n_d/2 doubles read + n_d/2 written
+  dev_free(ctx, buf);
+  return 0;
+}
+
 } // namespace femb200

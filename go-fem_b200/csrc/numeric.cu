@@ -260,6 +260,7 @@ struct NumArgs {
   double *values;             // CSR values of this call
   unsigned long long *err;
   const double *tab_g;
+  const double *h_tab;        // host copy of the table blob (C first)
   int offW, offN, offDN, nqp;
   int nu;                     // distinct dofmap values (== NDN when identity)
   int dof2u[kMaxNdn];
@@ -374,29 +375,62 @@ k_numeric_rows(const NumArgs a) {
 //
 //  k_geometry  -- "one batched per-element kernel": one thread per element evaluates, per quadrature
 //                 point, jac = dN*X, det (LU), the reference's error checks, J^-1 dN and the scale, and stages
-//                 the node values v_b[q] (see BT) plus f[q] = dJac*w*scale:  REC = nn*NV + 1 doubles per (e,q).
-//                 Errors are detected here, in element order (atomicMin on the packed error word).
-//  k_rows_dof  -- deterministic row reduction fused with the B^T C B products: one thread per scalar CSR row
-//                 (see the comment on the kernel).
-// Compared with the thread-per-node-row kernel above: NDN x more threads, NDN x less shared memory per
-// thread, no coordinate gathers or geometry in the row loop, no duplicated FP64 work.
+//                 the node values v_b[q] (see BT) plus f[q] = dJac*w*scale.  Record layout per (e, q):
+//                    NV == 3 :  [v0 v1 v2 f] per node  (32-byte aligned: one 256-bit load per node, f rides along)
+//                    else    :  [v_0 .. v_{nn-1} | f | pad]
+//                 Errors are detected here, in element order (atomicMin on the packed error word); elements with
+//                 a repeated node are flagged (degen[e]) for the ordered slow path of the row kernel.
+//  k_rows      -- deterministic row reduction fused with the B^T C B products (see the comment on the kernel).
 // =====================================================================================================
+__constant__ double c_C[kMaxDimC * kMaxDimC]; // constitutive matrix of the running call (row-major dimC x dimC)
+
+template <int BKIND, int D, int NN> struct Stag {
+  using B = BT<BKIND, D>;
+  static constexpr bool FIN = (B::NV == 3);                 // f stored in every node's 4th slot
+  static constexpr int NVP = FIN ? 4 : B::NV;               // doubles per node
+  static constexpr int REC = FIN ? NN * 4 : ((NN * B::NV + 2) & ~1);
+  static constexpr int FOFF = NN * B::NV;                   // !FIN: position of f
+};
+
+__device__ __forceinline__ void ld256(const double *p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int D, int NN, int BKIND, bool TAB_CONST>
 __global__ void __launch_bounds__(128)
 k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__restrict__ conn, double *__restrict__ stag,
-           unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp) {
+           uint8_t *__restrict__ degen, unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp) {
   using B = BT<BKIND, D>;
-  constexpr int NV = B::NV, REC = (NN * NV + 2) & ~1; // even: 16-byte aligned records
+  using S = Stag<BKIND, D, NN>;
+  constexpr int NV = B::NV, REC = S::REC;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_elem) return;
   Tab<TAB_CONST> tab{tab_g, offW, offN, offDN};
   double X[NN][D];
+  int32_t nid[NN];
+  if constexpr (NN % 4 == 0) {
+#pragma unroll
+    for (int v4 = 0; v4 < NN / 4; ++v4) {
+      const int4 w = __ldg(reinterpret_cast<const int4 *>(conn + e * NN) + v4);
+      nid[4 * v4] = w.x; nid[4 * v4 + 1] = w.y; nid[4 * v4 + 2] = w.z; nid[4 * v4 + 3] = w.w;
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < NN; ++b) nid[b] = __ldg(conn + e * NN + b);
+  }
+  bool dup = false;
 #pragma unroll
   for (int b = 0; b < NN; ++b) {
-    const int64_t nb = __ldg(conn + e * NN + b);
 #pragma unroll
-    for (int j = 0; j < D; ++j) X[b][j] = __ldg(nodes + nb * 3 + j);
+    for (int c = 0; c < b; ++c) dup = dup || (nid[b] == nid[c]);
+#pragma unroll
+    for (int j = 0; j < D; ++j) X[b][j] = __ldg(nodes + (int64_t)nid[b] * 3 + j);
   }
+  degen[e] = dup ? 1 : 0;
   for (int q = 0; q < nqp; ++q) {
     double inv[D][D], detJ, rinv, scale;
     const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
@@ -406,219 +440,261 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
       for (int m = 0; m < REC; ++m) rec[m] = 0.0;
       return; // the reference stops at the first failing quadrature point of the element (:95-107)
     }
+    const double f = detJ * tab.w(q) * scale; // (dJac*w)*scale, left to right (:111)
+    if constexpr (S::FIN) {
 #pragma unroll
-    for (int b = 0; b < NN; ++b) {
-      double vb[NV];
-      node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+      for (int b = 0; b < NN; ++b) {
+        double vb[NV];
+        node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+        st256(rec + 4 * b, vb[0], vb[1], vb[2], f);
+      }
+    } else {
+      double rv[REC];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) rec[b * NV + v] = vb[v];
+      for (int b = 0; b < NN; ++b) {
+        double vb[NV];
+        node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) rv[b * NV + v] = vb[v];
+      }
+      rv[S::FOFF] = f;
+      if constexpr (S::FOFF + 1 < REC) rv[S::FOFF + 1] = 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < REC / 2; ++c2) reinterpret_cast<double2 *>(rec)[c2] = make_double2(rv[2 * c2], rv[2 * c2 + 1]);
     }
-    rec[NN * NV] = detJ * tab.w(q) * scale; // (dJac*w)*scale, left to right (:111)
   }
 }
 
-struct DofArgs {
-  int64_t n_rows;             // n_nodes * NDN scalar rows
+struct RowArgs {
+  int64_t n_nodes;
   int64_t n_numeric;          // elements [n_numeric, n_elem) are pattern-only (halo): no values
   const int32_t *n2e_ptr;
   const uint32_t *n2e_t;
   const uint16_t *pos16;
   const int64_t *blkptr;
   const double *stag;
+  const uint8_t *degen;
   double *values;
-  const double *tab_g;
   int nqp;
 };
 
-// One thread per SCALAR CSR row r = NDN*I + i.  The thread walks the elements incident to node I in
-// ascending element index and adds row i of every block (a, b), b = 0..nn-1:
+// ---- the row kernel ------------------------------------------------------------------------------------
+// A group of G lanes owns one SCALAR CSR row r = NDN*I + i.  The group walks the elements incident to node I
+// in ascending element index and adds row i of every block (a, b), b = 0..nn-1:
 //     row_i(Ke[a][b]) = sum_q  (f * B_a[:, i]^T C)  B_b          (1 x NDN)
-// B_a[:, i] has at most NZ non-zeros, so the thread keeps the NZ rows of C it needs in registers for the
-// whole kernel (its i never changes) and E = f B_a[:,i]^T C costs NZ*DIMC FMAs, each block row NDN*<=3.
-// No work is duplicated between threads, no two threads ever touch the same accumulator (=> no atomics,
-// no barriers), and every K entry is summed in ascending element order: a deterministic segmented
-// reduction whose segments are the CSR rows.  Accumulators live in shared memory, interleaved by thread
-// (index m*T + tid): conflict free whatever column position each lane hits.
-template <int D, int NN, int BKIND, bool TAB_CONST, int TPB>
-__global__ void __launch_bounds__(TPB)
-k_rows_dof(const DofArgs a) {
+// Lane g of the group takes the element nodes b = g, g+G, ... and keeps their partial sums over the quadrature
+// points in FP64 registers; after the quadrature loop every lane adds its (distinct) column blocks into the
+// row's accumulators in shared memory.  Elements are processed one after the other by the whole group, so
+// every K entry is summed in ascending element order: a deterministic segmented reduction whose segments are
+// the CSR rows -- no atomics, no barriers wider than the group.
+//
+// The scalar row index i is WARP-UNIFORM (warp w of the block handles i = w % NDN), so the body is compiled
+// once per i: column i of B_a has one non-zero per node value v[m] (or none), its row of C is read straight
+// from the constant bank as a DFMA operand, and E = f * B_a[:, i]^T C costs NV*DIMC FMAs with no registers
+// spent on C.  Accumulators are interleaved by row in shared memory (index m*RPB + row): conflict free
+// for G = 1 whatever column each lane hits.
+template <int D, int NN, int BKIND, int G, int TPB>
+__device__ __forceinline__ void rows_body(const RowArgs &a, double *__restrict__ s_R, const int64_t I, const int i, const int g,
+                                          const int rloc, const unsigned gmask) {
   using B = BT<BKIND, D>;
-  constexpr int NDN = B::NDN, NV = B::NV, DIMC = B::DIMC, REC = (NN * NV + 2) & ~1, NPAIR = REC / 2;
-  constexpr int NZ = (BKIND == FEMB200_B_THERMAL || BKIND == FEMB200_B_THERMAL_AXISYM) ? DIMC : (BKIND == FEMB200_B_PLANE ? 2 : 3);
-  extern __shared__ double s_R[];
-  Tab<TAB_CONST> tab{a.tab_g, 0, 0, 0};
-  const int T = blockDim.x, tid = threadIdx.x;
-  const int64_t r = (int64_t)blockIdx.x * T + tid;
-  if (r >= a.n_rows) return;
-  const int64_t I = r / NDN;
-  const int i = (int)(r - I * NDN);
-  // non-zeros of column i of a node's B block: rows krow[m], value source ksrc[m] (index into v[])
-  int ksrc[NZ];
-  double Cr[NZ][DIMC];
-  {
-    int m = 0;
+  using S = Stag<BKIND, D, NN>;
+  constexpr int NDN = B::NDN, NV = B::NV, DIMC = B::DIMC, NVP = S::NVP, REC = S::REC;
+  constexpr int RPB = TPB / G;              // scalar rows per block
+  constexpr int NB = (NN + G - 1) / G;      // element nodes per lane
+  // Column i of a node's B block holds node value v[m] in row krow(i, m) (at most once); the thread keeps those
+  // NV rows of C in registers for the whole kernel (its i never changes): E = f B_a[:, i]^T C costs NV*DIMC FMAs.
+  double Cr[NV][DIMC];
 #pragma unroll
-    for (int k = 0; k < DIMC; ++k) {
-      int sk = -1;
+  for (int m = 0; m < NV; ++m) {
+    int kr = -1;
 #pragma unroll
-      for (int ii = 0; ii < NDN; ++ii) if (ii == i) sk = B::sel(k, ii);
-      if (sk >= 0 && m < NZ) {
-        // m is only known at run time (depends on i): write through a predicated unrolled select
+    for (int k = 0; k < DIMC; ++k)
 #pragma unroll
-        for (int mm = 0; mm < NZ; ++mm)
-          if (mm == m) {
-            ksrc[mm] = sk;
+      for (int ii = 0; ii < NDN; ++ii)
+        if (B::sel(k, ii) == m && ii == i) kr = k;
 #pragma unroll
-            for (int c = 0; c < DIMC; ++c) Cr[mm][c] = tab.template C<DIMC>(k, c);
-          }
-        ++m;
-      }
-    }
-#pragma unroll
-    for (int mm = 0; mm < NZ; ++mm)
-      if (mm >= m) {
-        ksrc[mm] = -1;
-#pragma unroll
-        for (int c = 0; c < DIMC; ++c) Cr[mm][c] = 0.0;
-      }
+    for (int c = 0; c < DIMC; ++c) Cr[m][c] = kr >= 0 ? c_C[kr * DIMC + c] : 0.0;
   }
-  const int beg = a.n2e_ptr[I], end = a.n2e_ptr[I + 1];
-  const int64_t b0 = a.blkptr[I];
-  const int rl = (int)(a.blkptr[I + 1] - b0);
-  if (rl == 0) return;                 // unreferenced node, or a row this rank does not assemble
+  const int beg = __ldg(a.n2e_ptr + I), end = __ldg(a.n2e_ptr + I + 1);
+  const int64_t b0 = __ldg(a.blkptr + I);
+  const int rl = (int)(__ldg(a.blkptr + I + 1) - b0);
+  if (rl == 0) return;                      // unreferenced node, or a row this rank does not assemble
   const int rowsz = rl * NDN;
-  for (int m = 0; m < rowsz; ++m) s_R[m * T + tid] = 0.0;
+  double *const sacc = s_R + rloc;          // accumulator m of this row: sacc[m * RPB]
+  for (int m = g; m < rowsz; m += G) sacc[m * RPB] = 0.0;
+  if constexpr (G > 1) __syncwarp(gmask);
+
+  const int64_t recsz = (int64_t)a.nqp * REC;
+  uint32_t ta = beg < end ? __ldg(a.n2e_t + beg) : 0u;
+  uint32_t tb = beg + 1 < end ? __ldg(a.n2e_t + beg + 1) : 0u;
+  if (beg + 1 < end) prefetch_l2(a.stag + (int64_t)(tb / NN) * recsz);
   for (int k = beg; k < end; ++k) {
-    const uint32_t t = __ldg(a.n2e_t + k);
+    const uint32_t t = ta;
+    ta = tb;
+    if (k + 2 < end) {
+      tb = __ldg(a.n2e_t + k + 2);
+      prefetch_l2(a.stag + (int64_t)(tb / NN) * recsz);
+    }
     const int64_t e = t / NN;
     if (e >= a.n_numeric) continue;
     const int la = (int)(t % NN);
-    // row-local slot positions of the element's nn nodes (the element->slot map), vector loads when aligned
-    int pos[NN];
-    if constexpr (NN % 4 == 0) {
-      const uint2 *pk2 = reinterpret_cast<const uint2 *>(a.pos16 + (int64_t)k * NN);
+    const bool dg = __ldg(a.degen + e) != 0;
+    // row-local slot positions of my element nodes (the element -> slot map)
+    int pos[NB];
+    const uint16_t *pk = a.pos16 + (int64_t)k * NN;
+    if constexpr (G == 1 && NN % 4 == 0) {
 #pragma unroll
       for (int v4 = 0; v4 < NN / 4; ++v4) {
-        const uint2 w = __ldg(pk2 + v4);
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(pk) + v4);
         pos[4 * v4] = w.x & 0xffff; pos[4 * v4 + 1] = w.x >> 16; pos[4 * v4 + 2] = w.y & 0xffff; pos[4 * v4 + 3] = w.y >> 16;
       }
     } else {
-      const uint16_t *pk = a.pos16 + (int64_t)k * NN;
 #pragma unroll
-      for (int b = 0; b < NN; ++b) pos[b] = __ldg(pk + b);
+      for (int s = 0; s < NB; ++s) pos[s] = (g + G * s < NN) ? (int)__ldg(pk + g + G * s) : 0;
     }
-    double acc[NN][NDN];
+    double acc[NB][NDN];
 #pragma unroll
-    for (int b = 0; b < NN; ++b)
+    for (int s = 0; s < NB; ++s)
 #pragma unroll
-      for (int j = 0; j < NDN; ++j) acc[b][j] = 0.0;
-    const double *rec = a.stag + e * a.nqp * REC;
+      for (int j = 0; j < NDN; ++j) acc[s][j] = 0.0;
+    const double *rec = a.stag + e * recsz;
     for (int q = 0; q < a.nqp; ++q, rec += REC) {
-      // the whole record with 16-byte loads: [v_0 .. v_{nn-1} | f | pad]
-      double rv[REC];
-      const double2 *rec2 = reinterpret_cast<const double2 *>(rec);
+      double va[NVP], f;
+      if constexpr (S::FIN) {
+        ld256(rec + 4 * la, va);
+        f = va[3];
+      } else {
 #pragma unroll
-      for (int c2 = 0; c2 < NPAIR; ++c2) {
-        const double2 w = __ldg(rec2 + c2);
-        rv[2 * c2] = w.x; rv[2 * c2 + 1] = w.y;
+        for (int m = 0; m < NV; ++m) va[m] = __ldg(rec + la * NV + m);
+        f = __ldg(rec + S::FOFF);
       }
-      const double f = rv[NN * NV];
       double E[DIMC];
 #pragma unroll
       for (int c = 0; c < DIMC; ++c) E[c] = 0.0;
 #pragma unroll
-      for (int m = 0; m < NZ; ++m) {
-        const double u = (ksrc[m] >= 0) ? __ldg(rec + la * NV + ksrc[m]) * f : 0.0; // run-time index: separate (L1-hit) load
+      for (int m = 0; m < NV; ++m) {
+        const double u = va[m] * f;
 #pragma unroll
         for (int c = 0; c < DIMC; ++c) E[c] = fma(u, Cr[m][c], E[c]);
       }
 #pragma unroll
-      for (int b = 0; b < NN; ++b) {
+      for (int s = 0; s < NB; ++s) {
+        const int b = g + G * s;
+        if (NN % G == 0 || b < NN) {
+          double vb[NVP];
+          if constexpr (S::FIN) {
+            ld256(rec + 4 * b, vb);
+          } else if constexpr (NVP == 2) {
+            const double2 w = __ldg(reinterpret_cast<const double2 *>(rec) + b);
+            vb[0] = w.x; vb[1] = w.y;
+          } else {
 #pragma unroll
-        for (int j = 0; j < NDN; ++j) {
-          double sj = acc[b][j];
+            for (int m = 0; m < NV; ++m) vb[m] = __ldg(rec + b * NV + m);
+          }
 #pragma unroll
-          for (int kk = 0; kk < DIMC; ++kk)
-            if (B::sel(kk, j) >= 0) sj = fma(E[kk], rv[b * NV + B::sel(kk, j)], sj);
-          acc[b][j] = sj;
+          for (int j = 0; j < NDN; ++j) {
+            double sj = acc[s][j];
+#pragma unroll
+            for (int kk = 0; kk < DIMC; ++kk)
+              if (B::sel(kk, j) >= 0) sj = fma(E[kk], vb[B::sel(kk, j)], sj);
+            acc[s][j] = sj;
+          }
         }
       }
     }
-    // Ordered accumulation.  The nn column blocks of one element are distinct unless the element is
-    // collapsed (a repeated node); when they are distinct all read-modify-writes are issued as one batch
-    // (loads, adds, stores) instead of nn dependent chains the compiler must assume may alias.
-    bool distinct = true;
-    if constexpr (NN <= 8) {
+    // Ordered accumulation.  The nn column blocks of one element are distinct unless the element is collapsed
+    // (a repeated node, flagged by k_geometry): then all read-modify-writes are issued as one batch.
+    if (!dg) {
+      double old[NB][NDN];
 #pragma unroll
-      for (int b = 1; b < NN; ++b)
+      for (int s = 0; s < NB; ++s)
 #pragma unroll
-        for (int c = 0; c < b; ++c) distinct = distinct && (pos[b] != pos[c]);
+        for (int j = 0; j < NDN; ++j) old[s][j] = sacc[(pos[s] * NDN + j) * RPB];
+#pragma unroll
+      for (int s = 0; s < NB; ++s)
+        if (NN % G == 0 || g + G * s < NN) {
+#pragma unroll
+          for (int j = 0; j < NDN; ++j) sacc[(pos[s] * NDN + j) * RPB] = old[s][j] + acc[s][j];
+        }
     } else {
-      distinct = false;
-    }
-    if (distinct) {
-      double old[NN][NDN];
+      // collapsed element: element nodes in ascending b, one at a time (same order as the reference's COO stream)
 #pragma unroll
-      for (int b = 0; b < NN; ++b)
+      for (int s = 0; s < NB; ++s) {
+#pragma unroll 1
+        for (int gg = 0; gg < G; ++gg) {
+          if (gg == g && g + G * s < NN) {
 #pragma unroll
-        for (int j = 0; j < NDN; ++j) old[b][j] = s_R[(pos[b] * NDN + j) * T + tid];
-#pragma unroll
-      for (int b = 0; b < NN; ++b)
-#pragma unroll
-        for (int j = 0; j < NDN; ++j) s_R[(pos[b] * NDN + j) * T + tid] = old[b][j] + acc[b][j];
-    } else {
-#pragma unroll
-      for (int b = 0; b < NN; ++b) {
-        double old[NDN];
-#pragma unroll
-        for (int j = 0; j < NDN; ++j) old[j] = s_R[(pos[b] * NDN + j) * T + tid];
-#pragma unroll
-        for (int j = 0; j < NDN; ++j) s_R[(pos[b] * NDN + j) * T + tid] = old[j] + acc[b][j];
+            for (int j = 0; j < NDN; ++j) sacc[(pos[s] * NDN + j) * RPB] += acc[s][j];
+          }
+          if constexpr (G > 1) __syncwarp(gmask);
+        }
       }
     }
+    if constexpr (G > 1) __syncwarp(gmask);
   }
   double *const vrow = a.values + (int64_t)NDN * NDN * b0 + (int64_t)i * rowsz;
-  for (int m = 0; m < rowsz; ++m) vrow[m] = s_R[m * T + tid];
+  for (int m = g; m < rowsz; m += G) vrow[m] = sacc[m * RPB];
 }
 
+template <int D, int NN, int BKIND, int G, int TPB>
+__global__ void __launch_bounds__(TPB)
+k_rows(const RowArgs a) {
+  using B = BT<BKIND, D>;
+  constexpr int NDN = B::NDN;
+  static_assert(TPB % 32 == 0 && 32 % G == 0, "G divides the warp");
+  constexpr int RPB = TPB / G;
+  extern __shared__ double s_R[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid % G, rloc = tid / G;
+  const int64_t r = (int64_t)blockIdx.x * RPB + rloc;   // consecutive lanes -> consecutive scalar rows: the NDN rows of a
+  if (r >= a.n_nodes * NDN) return;                      // node sit in neighbouring lanes and share every load
+  const int64_t I = r / NDN;
+  const int i = (int)(r - I * NDN);
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  rows_body<D, NN, BKIND, G, TPB>(a, s_R, I, i, g, rloc, gmask);
+}
+
+template <int NN> struct GroupOf { static constexpr int G = NN >= 20 ? 4 : (NN >= 8 ? 2 : 1); };
+
 template <int D, int NN, int BKIND, bool TAB_CONST>
-static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32, int64_t n_elem,
-                        SymbolicResult *sym) {
+static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, const int32_t *conn32,
+                        int64_t n_elem, SymbolicResult *sym) {
   femb200_ctx *ctx = ga->ctx;
   using B = BT<BKIND, D>;
-  constexpr int REC = (NN * B::NV + 2) & ~1;
+  using S = Stag<BKIND, D, NN>;
+  constexpr int G = GroupOf<NN>::G;
   constexpr int TPB = 128;
-  const size_t per_thread = (size_t)sym->max_rowlen * B::NDN * sizeof(double);
-  auto rows = k_rows_dof<D, NN, BKIND, TAB_CONST, TPB>;
+  constexpr int RPB = TPB / G;
+  const size_t smem = (size_t)sym->max_rowlen * B::NDN * sizeof(double) * RPB;
+  if (smem > ctx->smem_optin) return -2; // row too long for shared accumulators: caller falls back
+  auto rows = k_rows<D, NN, BKIND, G, TPB>;
   FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-  int bestT = 0, best_threads = 0;
-  const int cands[4] = {128, 96, 64, 32};
-  for (int c = 0; c < 4; ++c) {
-    const size_t need = per_thread * cands[c];
-    if (need > ctx->smem_optin) continue;
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rows, cands[c], need) != cudaSuccess) continue;
-    if (nb * cands[c] > best_threads) { best_threads = nb * cands[c]; bestT = cands[c]; }
-  }
-  if (bestT == 0) return -2;
+  FEMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_C, h_tab, sizeof(double) * sh.dimC * sh.dimC, 0, cudaMemcpyHostToDevice, ctx->stream));
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
   double *stag = nullptr;
-  int rc = dev_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * REC);
+  uint8_t *degen = nullptr;
+  int rc = dev_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * S::REC);
   if (rc) return rc;
+  if ((rc = dev_alloc(ctx, &degen, (size_t)n_elem))) return rc;
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
   if (n_elem) {
-    k_geometry<D, NN, BKIND, TAB_CONST><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, ga->d_nodes, conn32, stag, ctx->d_err, d_tab,
+    k_geometry<D, NN, BKIND, TAB_CONST><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, ga->d_nodes, conn32, stag, degen, ctx->d_err, d_tab,
                                                                                       tl.offW, tl.offN, tl.offDN, sh.nqp);
     ctx->launches++;
   }
-  DofArgs a;
-  a.n_rows = ga->n_nodes * B::NDN; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
-  a.stag = stag; a.values = sym->csr.values; a.tab_g = d_tab; a.nqp = sh.nqp;
-  if (a.n_rows) {
-    rows<<<grid_for(a.n_rows, bestT), bestT, per_thread * bestT, ctx->stream>>>(a);
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
+  RowArgs a;
+  a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
+  a.stag = stag; a.degen = degen; a.values = sym->csr.values; a.nqp = sh.nqp;
+  if (a.n_nodes) {
+    rows<<<grid_for(a.n_nodes * B::NDN, RPB), TPB, smem, ctx->stream>>>(a);
     ctx->launches++;
   }
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
+  ga->split_numeric = true;
   FEMB_CUDA_OK(ctx, cudaGetLastError());
   dev_free(ctx, stag);
+  dev_free(ctx, degen);
   return 0;
 }
 
@@ -663,8 +739,8 @@ static int launch_rows(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, b
   const bool force_global = getenv("FEMB200_FORCE_GLOBAL_ACC") != nullptr;
   const bool force_thread_rows = getenv("FEMB200_FORCE_THREAD_ROWS") != nullptr;
   if (sh.identity && !force_global && !force_thread_rows) {
-    rc = tab_const ? launch_dof_T<D, NN, BKIND, true>(ga, sh, a.tab_g, a.conn, n_elem, sym)
-                   : launch_dof_T<D, NN, BKIND, false>(ga, sh, a.tab_g, a.conn, n_elem, sym);
+    rc = tab_const ? launch_dof_T<D, NN, BKIND, true>(ga, sh, a.tab_g, a.h_tab, a.conn, n_elem, sym)
+                   : launch_dof_T<D, NN, BKIND, false>(ga, sh, a.tab_g, a.h_tab, a.conn, n_elem, sym);
     if (rc != -2) return rc;
   }
   if (sh.identity && !force_global)
@@ -730,6 +806,7 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
   a.values = sym->csr.values;
   a.err = ctx->d_err;
   a.tab_g = d_tab;
+  a.h_tab = h_tab;
   a.offW = tl.offW; a.offN = tl.offN; a.offDN = tl.offDN; a.nqp = sh.nqp;
   a.nu = sh.nu;
   for (int i = 0; i < kMaxNdn; ++i) a.dof2u[i] = sh.dof2u[i];

@@ -159,13 +159,18 @@ int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc
 
 /* Device-side phase timers of the last add call, milliseconds (CUDA events on the context stream):
  * [0] upload+validate [1] node->element adjacency [2] row pattern [3] CSR expand
- * [4] numeric + row reduction [5] merge into K [6] total device [7] numeric kernel launches in total. */
-#define FEMB200_N_TIMERS 8
+ * [4] numeric + row reduction [5] merge into K [6] total device [7] numeric kernel launches in total
+ * [8] of [4]: the batched per-element geometry kernel  [9] of [4]: the row kernel (B^T C B + reduction). */
+#define FEMB200_N_TIMERS 10
 int femb200_phase_ms(const femb200_assembler *ga, float out[FEMB200_N_TIMERS]);
 /* Number of kernels this library launched since the context was created (bench.py "gpu_launches"). */
 int64_t femb200_kernel_launches(const femb200_ctx *ctx);
 /* Blocks until all work queued on the context stream is done. */
 int femb200_sync(femb200_ctx *ctx);
+/* Roofline denominators measured on this device (no reference counterpart; used by bench.py only):
+ * out[0] = FP64 vector peak in TFLOP/s (independent DFMA chains, all SMs), out[1] = HBM copy bandwidth in GB/s
+ * (read + write bytes of a 1 GiB device-to-device copy kernel), both best of `reps` CUDA-event timings. */
+int femb200_probe_peaks(femb200_ctx *ctx, int32_t reps, double out[2]);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ for it in range(6):
     h = C.c_void_p()
     L.femb200_assembler_create(ra.ctx, C.c_void_p(w["nodes"].ctypes.data), w["nodes"].shape[0], w["ndn"], 0, C.byref(h))
     rc = L.femb200_add_isoparametric(h, C.byref(desc), C.c_void_p(conn32.ctypes.data), 0, 0, conn32.shape[0])
-    ph = (C.c_float * 8)(); L.femb200_phase_ms(h, ph)
+    ph = (C.c_float * pkg.N_TIMERS)(); L.femb200_phase_ms(h, ph)
     L.femb200_assembler_destroy(h)
     if it >= 2: res.append([float(x) for x in ph])
 m = np.mean(res, axis=0)
