@@ -14,6 +14,8 @@
 // sum, i.e. a deterministic segmented reduction whose segments are the CSR rows.  HBM traffic is the
 // compulsory one: connectivity + coordinates (L2 resident) in, CSR values out.
 #include "common.cuh"
+#include <type_traits>
+#include <cstdlib>
 
 namespace femb200 {
 
@@ -475,72 +477,102 @@ struct RowArgs {
   const double *stag;
   const uint8_t *degen;
   double *values;
+  int64_t ninc;               // n_elem * nn (length of n2e_t)
   int nqp;
+  int dbg;                    // FEMB200_DBG experiment bits (0 in production)
 };
 
-// ---- the row kernel ------------------------------------------------------------------------------------
-// A group of G lanes owns one SCALAR CSR row r = NDN*I + i.  The group walks the elements incident to node I
-// in ascending element index and adds row i of every block (a, b), b = 0..nn-1:
-//     row_i(Ke[a][b]) = sum_q  (f * B_a[:, i]^T C)  B_b          (1 x NDN)
-// Lane g of the group takes the element nodes b = g, g+G, ... and keeps their partial sums over the quadrature
-// points in FP64 registers; after the quadrature loop every lane adds its (distinct) column blocks into the
-// row's accumulators in shared memory.  Elements are processed one after the other by the whole group, so
-// every K entry is summed in ascending element order: a deterministic segmented reduction whose segments are
-// the CSR rows -- no atomics, no barriers wider than the group.
-//
-// The scalar row index i is WARP-UNIFORM (warp w of the block handles i = w % NDN), so the body is compiled
-// once per i: column i of B_a has one non-zero per node value v[m] (or none), its row of C is read straight
-// from the constant bank as a DFMA operand, and E = f * B_a[:, i]^T C costs NV*DIMC FMAs with no registers
-// spent on C.  Accumulators are interleaved by row in shared memory (index m*RPB + row): conflict free
-// for G = 1 whatever column each lane hits.
+// ---- the node-row kernel (default) ----------------------------------------------------------------------
+// A group of G lanes owns one NODE-BLOCK row I of K, i.e. the NDN scalar CSR rows of node I at once.  Compared
+// with k_rows (one scalar row per group) every staged record is loaded once instead of NDN times, the scalar
+// row index i is a compile-time loop (so column i of B_a is known statically and its rows of C are read
+// straight from the constant bank as DFMA operands: no registers spent on C), and the block needs NDN times
+// fewer threads for the same shared-memory accumulators.  Everything else is as in k_rows: lane g takes the
+// element nodes b = g, g+G, ..., keeps their partial sums over the quadrature points in FP64 registers, and
+// after the quadrature loop adds its (distinct) column blocks into the row accumulators in shared memory;
+// elements are visited in ascending index by the whole group => deterministic segmented reduction, no atomics.
+// Loads run one step ahead of the arithmetic through two register buffers (A/B, swapped by unrolling the step
+// loop by two), incidence ids three elements ahead, L2 prefetch of the staged record two elements ahead.
+// Accumulators: entry m of node slot n at s_R[m * NPBP + n], NPBP odd => the per-lane read-modify-writes and
+// the warp-cooperative, fully coalesced copy-out of the finished rows are both bank-conflict free.
+template <int BKIND, int D, int I_, int M_> struct KRow { // row k of B with sel(k, I_) == M_  (-1: none)
+  static constexpr int value() {
+    using B = BT<BKIND, D>;
+    int kr = -1;
+    for (int k = 0; k < B::DIMC; ++k)
+      if (B::sel(k, I_) == M_) kr = k;
+    return kr;
+  }
+};
+
+template <int BKIND, int D, int I_, int M_>
+__device__ __forceinline__ void e_row_add(double u, double (&E)[BT<BKIND, D>::DIMC]) {
+  constexpr int KR = KRow<BKIND, D, I_, M_>::value();
+  constexpr int DIMC = BT<BKIND, D>::DIMC;
+  if constexpr (KR >= 0) {
+#pragma unroll
+    for (int c = 0; c < DIMC; ++c) E[c] = fma(u, c_C[KR * DIMC + c], E[c]);
+  }
+}
+
 template <int D, int NN, int BKIND, int G, int TPB>
-__device__ __forceinline__ void rows_body(const RowArgs &a, double *__restrict__ s_R, const int64_t I, const int i, const int g,
-                                          const int rloc, const unsigned gmask) {
+__global__ void __launch_bounds__(TPB)
+k_noderows(const RowArgs a) {
   using B = BT<BKIND, D>;
   using S = Stag<BKIND, D, NN>;
   constexpr int NDN = B::NDN, NV = B::NV, DIMC = B::DIMC, NVP = S::NVP, REC = S::REC;
-  constexpr int RPB = TPB / G;              // scalar rows per block
+  static_assert(TPB % 32 == 0 && 32 % G == 0, "G divides the warp");
+  constexpr int NPB = TPB / G;              // node rows per block
+  constexpr int NPBP = NPB | 1;             // padded (odd) stride of the shared accumulators
+  constexpr int NPW = 32 / G;               // node rows per warp
   constexpr int NB = (NN + G - 1) / G;      // element nodes per lane
-  // Column i of a node's B block holds node value v[m] in row krow(i, m) (at most once); the thread keeps those
-  // NV rows of C in registers for the whole kernel (its i never changes): E = f B_a[:, i]^T C costs NV*DIMC FMAs.
-  double Cr[NV][DIMC];
-#pragma unroll
-  for (int m = 0; m < NV; ++m) {
-    int kr = -1;
-#pragma unroll
-    for (int k = 0; k < DIMC; ++k)
-#pragma unroll
-      for (int ii = 0; ii < NDN; ++ii)
-        if (B::sel(k, ii) == m && ii == i) kr = k;
-#pragma unroll
-    for (int c = 0; c < DIMC; ++c) Cr[m][c] = kr >= 0 ? c_C[kr * DIMC + c] : 0.0;
+  extern __shared__ double s_R[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid % G, nloc = tid / G;
+  const int64_t I = (int64_t)blockIdx.x * NPB + nloc;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  int beg = 0, end = 0, rl = 0;
+  int64_t b0 = 0;
+  if (I < a.n_nodes) {
+    beg = __ldg(a.n2e_ptr + I); end = __ldg(a.n2e_ptr + I + 1);
+    b0 = __ldg(a.blkptr + I);
+    rl = (int)(__ldg(a.blkptr + I + 1) - b0);
   }
-  const int beg = __ldg(a.n2e_ptr + I), end = __ldg(a.n2e_ptr + I + 1);
-  const int64_t b0 = __ldg(a.blkptr + I);
-  const int rl = (int)(__ldg(a.blkptr + I + 1) - b0);
-  if (rl == 0) return;                      // unreferenced node, or a row this rank does not assemble
-  const int rowsz = rl * NDN;
-  double *const sacc = s_R + rloc;          // accumulator m of this row: sacc[m * RPB]
-  for (int m = g; m < rowsz; m += G) sacc[m * RPB] = 0.0;
+  if (rl == 0) end = beg;                   // unreferenced node, or a row this rank does not assemble
+  const int rowsz = rl * NDN;               // scalar row length
+  const int tot = rowsz * NDN;              // entries of the node-block row: [i][p][j]
+  double *const sacc = s_R + nloc;
+  for (int m = g; m < tot; m += G) sacc[m * NPBP] = 0.0;
   if constexpr (G > 1) __syncwarp(gmask);
 
   const int64_t recsz = (int64_t)a.nqp * REC;
-  uint32_t ta = beg < end ? __ldg(a.n2e_t + beg) : 0u;
-  uint32_t tb = beg + 1 < end ? __ldg(a.n2e_t + beg + 1) : 0u;
-  if (beg + 1 < end) prefetch_l2(a.stag + (int64_t)(tb / NN) * recsz);
-  for (int k = beg; k < end; ++k) {
-    const uint32_t t = ta;
-    ta = tb;
-    if (k + 2 < end) {
-      tb = __ldg(a.n2e_t + k + 2);
-      prefetch_l2(a.stag + (int64_t)(tb / NN) * recsz);
+  struct Buf { double va[NVP]; double f; double vb[NB][NVP]; };
+  auto load_rec = [&](const double *rec, int la, Buf &o) {
+    if constexpr (S::FIN) {
+      ld256(rec + 4 * la, o.va);
+      o.f = 0.0; // rides in va[3]
+    } else {
+      const double2 w = __ldg(reinterpret_cast<const double2 *>(rec) + la);
+      o.va[0] = w.x; o.va[1] = w.y;
+      o.f = __ldg(rec + S::FOFF);
     }
-    const int64_t e = t / NN;
-    if (e >= a.n_numeric) continue;
-    const int la = (int)(t % NN);
-    const bool dg = __ldg(a.degen + e) != 0;
-    // row-local slot positions of my element nodes (the element -> slot map)
-    int pos[NB];
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+      const int b = g + G * s;
+      if (NN % G == 0 || b < NN) {
+        if constexpr (S::FIN) {
+          ld256(rec + 4 * b, o.vb[s]);
+        } else {
+          const double2 w = __ldg(reinterpret_cast<const double2 *>(rec) + b);
+          o.vb[s][0] = w.x; o.vb[s][1] = w.y;
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < NVP; ++m) o.vb[s][m] = 0.0;
+      }
+    }
+  };
+  auto load_pos = [&](int k, int (&pos)[NB]) {
     const uint16_t *pk = a.pos16 + (int64_t)k * NN;
     if constexpr (G == 1 && NN % 4 == 0) {
 #pragma unroll
@@ -552,70 +584,119 @@ __device__ __forceinline__ void rows_body(const RowArgs &a, double *__restrict__
 #pragma unroll
       for (int s = 0; s < NB; ++s) pos[s] = (g + G * s < NN) ? (int)__ldg(pk + g + G * s) : 0;
     }
-    double acc[NB][NDN];
+  };
+
+  // ---- pipeline state ------------------------------------------------------------------------------------
+  // incidence lists are ascending in element index and pattern-only (halo) elements come last: the first halo
+  // incidence ends the row's numeric work
+  int kend = end, k = beg, q = 0, la = 0;
+  uint32_t tA = beg < end ? __ldg(a.n2e_t + beg) : 0u;         // id of incidence k
+  uint32_t tB = beg + 1 < end ? __ldg(a.n2e_t + beg + 1) : 0u; // k+1
+  uint32_t tC = beg + 2 < end ? __ldg(a.n2e_t + beg + 2) : 0u; // k+2
+  uint32_t tD = 0u;                                            // k+3, in flight
+  if (beg < end && (int64_t)(tA / NN) >= a.n_numeric) kend = beg;
+  bool more = false;
+  const double *rec = a.stag;
+  Buf bufA, bufB;
+  int pos[NB], posn[NB];
+#pragma unroll
+  for (int s = 0; s < NB; ++s) { pos[s] = 0; posn[s] = 0; }
+  bool dg = false, dgn = false;
+  double acc[NDN][NB][NDN];
+#pragma unroll
+  for (int i = 0; i < NDN; ++i)
 #pragma unroll
     for (int s = 0; s < NB; ++s)
 #pragma unroll
-      for (int j = 0; j < NDN; ++j) acc[s][j] = 0.0;
-    const double *rec = a.stag + e * recsz;
-    for (int q = 0; q < a.nqp; ++q, rec += REC) {
-      double va[NVP], f;
-      if constexpr (S::FIN) {
-        ld256(rec + 4 * la, va);
-        f = va[3];
-      } else {
+      for (int j = 0; j < NDN; ++j) acc[i][s][j] = 0.0;
+
+  // bookkeeping at the start of element k (ids tA, tB, tC are in registers)
+  auto begin_element = [&]() {
+    la = (int)(tA % NN);
+    if (k + 3 < end) tD = __ldg(a.n2e_t + k + 3);
+    if (k + 2 < end) {
+      const char *pr = reinterpret_cast<const char *>(a.stag + (int64_t)(tC / NN) * recsz);
 #pragma unroll
-        for (int m = 0; m < NV; ++m) va[m] = __ldg(rec + la * NV + m);
-        f = __ldg(rec + S::FOFF);
-      }
+      for (int ln = 0; ln < (REC * 8 + 127) / 128 && ln < 4; ++ln) prefetch_l2(pr + 128 * ln);
+    }
+    // the slot map and the incidence list are streamed: touch the line two lines ahead when a new line starts
+    if (((k * NN * 2) & 127) < NN * 2 && (int64_t)k * NN + 128 < a.ninc * NN) prefetch_l2(a.pos16 + (int64_t)k * NN + 128);
+    if ((k & 31) == 0 && k + 64 < a.ninc) prefetch_l2(a.n2e_t + k + 64);
+    more = (k + 1 < kend) && ((int64_t)(tB / NN) < a.n_numeric);
+    if (k + 1 < kend && !more) kend = k + 1;
+  };
+  if (k < kend) {
+    rec = a.stag + (int64_t)(tA / NN) * recsz;
+    load_rec(rec, (int)(tA % NN), bufA);
+    load_pos(k, pos);
+    dg = __ldg(a.degen + tA / NN) != 0;
+    if (beg + 1 < end) prefetch_l2(a.stag + (int64_t)(tB / NN) * recsz);
+    begin_element();
+  }
+
+  auto step = [&](Buf &cur, Buf &nxt) {
+    // 1. issue the loads of the next step
+    const bool last_q = (q + 1 == a.nqp);
+    const double *recn = rec;
+    if (!last_q) {
+      load_rec(rec + (int64_t)(q + 1) * REC, la, nxt);
+    } else if (more) {
+      recn = a.stag + (int64_t)(tB / NN) * recsz;
+      load_rec(recn, (int)(tB % NN), nxt);
+      load_pos(k + 1, posn);
+      dgn = __ldg(a.degen + tB / NN) != 0;
+    }
+    // 2. row i of every block (a, b) of this quadrature point, i = 0..NDN-1
+    const double f = S::FIN ? cur.va[NVP - 1] : cur.f;
+    double u[NV];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) u[m] = cur.va[m] * f;
+    auto row = [&](auto ic) {
+      constexpr int I_ = decltype(ic)::value;
       double E[DIMC];
 #pragma unroll
       for (int c = 0; c < DIMC; ++c) E[c] = 0.0;
-#pragma unroll
-      for (int m = 0; m < NV; ++m) {
-        const double u = va[m] * f;
-#pragma unroll
-        for (int c = 0; c < DIMC; ++c) E[c] = fma(u, Cr[m][c], E[c]);
-      }
+      e_row_add<BKIND, D, I_, 0>(u[0], E);
+      if constexpr (NV > 1) e_row_add<BKIND, D, I_, (NV > 1 ? 1 : 0)>(u[NV > 1 ? 1 : 0], E);
+      if constexpr (NV > 2) e_row_add<BKIND, D, I_, (NV > 2 ? 2 : 0)>(u[NV > 2 ? 2 : 0], E);
 #pragma unroll
       for (int s = 0; s < NB; ++s) {
-        const int b = g + G * s;
-        if (NN % G == 0 || b < NN) {
-          double vb[NVP];
-          if constexpr (S::FIN) {
-            ld256(rec + 4 * b, vb);
-          } else if constexpr (NVP == 2) {
-            const double2 w = __ldg(reinterpret_cast<const double2 *>(rec) + b);
-            vb[0] = w.x; vb[1] = w.y;
-          } else {
-#pragma unroll
-            for (int m = 0; m < NV; ++m) vb[m] = __ldg(rec + b * NV + m);
-          }
+        if (NN % G == 0 || g + G * s < NN) {
 #pragma unroll
           for (int j = 0; j < NDN; ++j) {
-            double sj = acc[s][j];
+            double sj = acc[I_][s][j];
 #pragma unroll
             for (int kk = 0; kk < DIMC; ++kk)
-              if (B::sel(kk, j) >= 0) sj = fma(E[kk], vb[B::sel(kk, j)], sj);
-            acc[s][j] = sj;
+              if (B::sel(kk, j) >= 0) sj = fma(E[kk], cur.vb[s][B::sel(kk, j)], sj);
+            acc[I_][s][j] = sj;
           }
         }
       }
-    }
-    // Ordered accumulation.  The nn column blocks of one element are distinct unless the element is collapsed
-    // (a repeated node, flagged by k_geometry): then all read-modify-writes are issued as one batch.
-    if (!dg) {
-      double old[NB][NDN];
+    };
+    row(std::integral_constant<int, 0>{});
+    if constexpr (NDN > 1) row(std::integral_constant<int, (NDN > 1 ? 1 : 0)>{});
+    if constexpr (NDN > 2) row(std::integral_constant<int, (NDN > 2 ? 2 : 0)>{});
+    if (!last_q) { ++q; return; }
+    // 3. end of the element: ordered accumulation into the shared row accumulators.  The nn column blocks of
+    // one element are distinct unless the element is collapsed (a repeated node, flagged by k_geometry).
+    if (a.dbg & 2) {
+      if (acc[0][0][0] == 1.2345) sacc[0] = 1.0;
+    } else if (!dg) {
 #pragma unroll
-      for (int s = 0; s < NB; ++s)
+      for (int i = 0; i < NDN; ++i) {
+        double old[NB][NDN];
+        double *const srow = sacc + i * rowsz * NPBP;
 #pragma unroll
-        for (int j = 0; j < NDN; ++j) old[s][j] = sacc[(pos[s] * NDN + j) * RPB];
+        for (int s = 0; s < NB; ++s)
 #pragma unroll
-      for (int s = 0; s < NB; ++s)
-        if (NN % G == 0 || g + G * s < NN) {
+          for (int j = 0; j < NDN; ++j) old[s][j] = srow[(pos[s] * NDN + j) * NPBP];
 #pragma unroll
-          for (int j = 0; j < NDN; ++j) sacc[(pos[s] * NDN + j) * RPB] = old[s][j] + acc[s][j];
-        }
+        for (int s = 0; s < NB; ++s)
+          if (NN % G == 0 || g + G * s < NN) {
+#pragma unroll
+            for (int j = 0; j < NDN; ++j) srow[(pos[s] * NDN + j) * NPBP] = old[s][j] + acc[i][s][j];
+          }
+      }
     } else {
       // collapsed element: element nodes in ascending b, one at a time (same order as the reference's COO stream)
 #pragma unroll
@@ -624,37 +705,71 @@ __device__ __forceinline__ void rows_body(const RowArgs &a, double *__restrict__
         for (int gg = 0; gg < G; ++gg) {
           if (gg == g && g + G * s < NN) {
 #pragma unroll
-            for (int j = 0; j < NDN; ++j) sacc[(pos[s] * NDN + j) * RPB] += acc[s][j];
+            for (int i = 0; i < NDN; ++i)
+#pragma unroll
+              for (int j = 0; j < NDN; ++j) sacc[(i * rowsz + pos[s] * NDN + j) * NPBP] += acc[i][s][j];
           }
           if constexpr (G > 1) __syncwarp(gmask);
         }
       }
     }
     if constexpr (G > 1) __syncwarp(gmask);
+#pragma unroll
+    for (int i = 0; i < NDN; ++i)
+#pragma unroll
+      for (int s = 0; s < NB; ++s)
+#pragma unroll
+        for (int j = 0; j < NDN; ++j) acc[i][s][j] = 0.0;
+    // advance to element k+1
+    ++k; q = 0;
+    tA = tB; tB = tC; tC = tD;
+    rec = recn;
+#pragma unroll
+    for (int s = 0; s < NB; ++s) pos[s] = posn[s];
+    dg = dgn;
+    if (k < kend) begin_element();
+  };
+  while (k < kend) {
+    step(bufA, bufB);
+    if (!(k < kend)) break;
+    step(bufB, bufA);
   }
-  double *const vrow = a.values + (int64_t)NDN * NDN * b0 + (int64_t)i * rowsz;
-  for (int m = g; m < rowsz; m += G) vrow[m] = sacc[m * RPB];
+
+  // ---- copy-out: the node rows of one warp are contiguous in the CSR values; every lane of the warp helps
+  // with every row => 256-byte coalesced stores
+  __syncwarp();
+  double *const vbase = a.values + (int64_t)NDN * NDN * b0;
+  if (a.dbg & 1) { if (sacc[0] == 1.2345) vbase[0] = 1.0; return; }
+#pragma unroll 1
+  for (int n = 0; n < NPW; ++n) {
+    const int tot_n = __shfl_sync(0xffffffffu, tot, n * G);
+    const unsigned long long vb_n = __shfl_sync(0xffffffffu, (unsigned long long)vbase, n * G);
+    const int nloc_n = __shfl_sync(0xffffffffu, nloc, n * G);
+    double *const vrow = reinterpret_cast<double *>(vb_n);
+    const double *const src = s_R + nloc_n;
+    for (int m = lane; m < tot_n; m += 32) vrow[m] = src[m * NPBP];
+  }
 }
 
-template <int D, int NN, int BKIND, int G, int TPB>
-__global__ void __launch_bounds__(TPB)
-k_rows(const RowArgs a) {
+// lanes per node row: default per element size, FEMB200_G overrides (tuning); larger G = less shared memory per block
+template <int NN> struct GroupOf { static constexpr int G = NN >= 8 ? 4 : (NN >= 4 ? 2 : 1); };
+
+template <int D, int NN, int BKIND, int G>
+static int launch_noderows(femb200_ctx *ctx, const RowArgs &a, int max_rowlen) {
   using B = BT<BKIND, D>;
-  constexpr int NDN = B::NDN;
-  static_assert(TPB % 32 == 0 && 32 % G == 0, "G divides the warp");
-  constexpr int RPB = TPB / G;
-  extern __shared__ double s_R[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int g = tid % G, rloc = tid / G;
-  const int64_t r = (int64_t)blockIdx.x * RPB + rloc;   // consecutive lanes -> consecutive scalar rows: the NDN rows of a
-  if (r >= a.n_nodes * NDN) return;                      // node sit in neighbouring lanes and share every load
-  const int64_t I = r / NDN;
-  const int i = (int)(r - I * NDN);
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-  rows_body<D, NN, BKIND, G, TPB>(a, s_R, I, i, g, rloc, gmask);
+  constexpr int TPN = 32;                        // one warp per block
+  constexpr int NPBP = (TPN / G) | 1;
+  const size_t smem = (size_t)max_rowlen * B::NDN * B::NDN * sizeof(double) * NPBP;
+  if (smem > ctx->smem_optin) return -2;
+  auto nrows = k_noderows<D, NN, BKIND, G, TPN>;
+  FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(nrows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  if (a.n_nodes) {
+    nrows<<<grid_for(a.n_nodes, TPN / G), TPN, smem, ctx->stream>>>(a);
+    ctx->launches++;
+  }
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
 }
-
-template <int NN> struct GroupOf { static constexpr int G = NN >= 20 ? 4 : (NN >= 8 ? 2 : 1); };
 
 template <int D, int NN, int BKIND, bool TAB_CONST>
 static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, const int32_t *conn32,
@@ -662,13 +777,15 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   femb200_ctx *ctx = ga->ctx;
   using B = BT<BKIND, D>;
   using S = Stag<BKIND, D, NN>;
-  constexpr int G = GroupOf<NN>::G;
-  constexpr int TPB = 128;
-  constexpr int RPB = TPB / G;
-  const size_t smem = (size_t)sym->max_rowlen * B::NDN * sizeof(double) * RPB;
-  if (smem > ctx->smem_optin) return -2; // row too long for shared accumulators: caller falls back
-  auto rows = k_rows<D, NN, BKIND, G, TPB>;
-  FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  constexpr int G0 = GroupOf<NN>::G;
+  constexpr int G1 = (2 * G0 <= NN) ? 2 * G0 : G0, G2 = (4 * G0 <= NN && NN < 8) ? 4 * G0 : G1; // fallbacks with smaller blocks
+  int gsel = getenv("FEMB200_G") ? atoi(getenv("FEMB200_G")) : G0;
+  if (gsel != G0 && gsel != G1 && gsel != G2) gsel = G0;
+  {
+    // does any variant fit the shared-memory accumulators?  (the smallest block is the one with the most lanes per row)
+    const size_t smem_min = (size_t)sym->max_rowlen * B::NDN * B::NDN * sizeof(double) * ((32 / G2) | 1);
+    if (smem_min > ctx->smem_optin) return -2; // caller falls back to global accumulators
+  }
   FEMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_C, h_tab, sizeof(double) * sh.dimC * sh.dimC, 0, cudaMemcpyHostToDevice, ctx->stream));
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
   double *stag = nullptr;
@@ -685,17 +802,17 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
   RowArgs a;
   a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
-  a.stag = stag; a.degen = degen; a.values = sym->csr.values; a.nqp = sh.nqp;
-  if (a.n_nodes) {
-    rows<<<grid_for(a.n_nodes * B::NDN, RPB), TPB, smem, ctx->stream>>>(a);
-    ctx->launches++;
-  }
+  a.stag = stag; a.degen = degen; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
+  a.dbg = getenv("FEMB200_DBG") ? atoi(getenv("FEMB200_DBG")) : 0;
+  rc = -2;
+  if (gsel == G0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym->max_rowlen);
+  if (rc == -2 && gsel <= G1) rc = launch_noderows<D, NN, BKIND, G1>(ctx, a, sym->max_rowlen);
+  if (rc == -2) rc = launch_noderows<D, NN, BKIND, G2>(ctx, a, sym->max_rowlen);
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
   ga->split_numeric = true;
-  FEMB_CUDA_OK(ctx, cudaGetLastError());
   dev_free(ctx, stag);
   dev_free(ctx, degen);
-  return 0;
+  return rc;
 }
 
 // ---- launch plumbing -------------------------------------------------------------------------------
