@@ -212,9 +212,15 @@ def make_workload_desc(name, size):
 
 def run_multi_gpu(args, rank, world, local_rank):
     """N > 1: weak scaling.  Global mesh = BCC box of (48*N) x 48 x 48 cells (N x config 1); elements in cell-major
-    (space-filling) order are split into N contiguous chunks, one per GPU.  A step = local assembly of the chunk
-    (symbolic + numeric, inputs resident in HBM) + the NCCL exchange of interface rows that leaves every GPU owning
-    its row block of the distributed CSR K.  Timed with CUDA events on the single stream everything runs on."""
+    (space-filling) order are split into N contiguous chunks, one per GPU; a node (row block) belongs to the lowest
+    rank touching it.  A step = local assembly of the chunk (symbolic + numeric, inputs resident in HBM) + the
+    exchange that leaves every GPU owning its row block of the distributed CSR K:
+      exchange (headline, the north star's scheme): owned rows assembled from [own elements ; halo elements (pattern
+        only)], interface rows assembled from the own elements touching foreign nodes, packed per owner, ONE NCCL
+        all-to-all over NVLink (sizes fixed by the partition plan), added in place in ascending source rank;
+      owner_computes (reported alongside): halo elements are assembled numerically by the owner as well -- redundant
+        O(surface) work, no collective at all, rows bit-identical to the single-GPU result.
+    Timed with CUDA events on the single stream everything runs on, max over ranks."""
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -228,21 +234,37 @@ def run_multi_gpu(args, rank, world, local_rank):
     ne_total = conn.shape[0]
     bounds = D.chunk_bounds(ne_total, world)
     plan = D.ExchangePlan(nodes.shape[0], conn, bounds, rank, 3)
+    iplan = D.InterfacePlan(plan, nodes.shape[0], conn, bounds, 3, dist)
     lconn, nhalo = plan.local_connectivity(conn, bounds)
     my = np.ascontiguousarray(lconn.astype(np.int32))
     own_conn = conn[bounds[rank]:bounds[rank + 1]]
     out_conn = np.ascontiguousarray(own_conn[plan.send_elems].astype(np.int32))
+    # owner-computes variant: own + halo elements in ascending GLOBAL element index (same summation order as 1 GPU)
+    gids = np.concatenate([np.arange(bounds[rank], bounds[rank + 1]), plan.halo_elems])
+    ghost = np.ascontiguousarray(conn[np.sort(gids)].astype(np.int32))
     d_nodes = torch.from_numpy(nodes).to(dev)
     d_conn = torch.from_numpy(my).to(dev)
+    d_ghost = torch.from_numpy(ghost).to(dev)
     d_out = torch.from_numpy(out_conn).to(dev) if out_conn.size else torch.zeros(4, dtype=torch.int32, device=dev)
     m_own = torch.as_tensor(plan.own_node_mask, device=dev)
     m_send = torch.as_tensor(plan.send_node_mask, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     elemT, c = pkg.elements.Tetra4(), pkg.solids.Isotropic(E_MOD, NU).Solid3D()
+    # two library contexts per rank, one stream and one host thread each: the owned row block and the (small) set of
+    # outgoing interface rows are assembled concurrently, the second call filling the gaps of the first
+    from concurrent.futures import ThreadPoolExecutor
     holder = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=nodes.shape[0])
+    holder_b = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=nodes.shape[0])
     L = pkg.lib()
-    L.femb200_ctx_set_stream(holder.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    s0 = torch.cuda.current_stream()
+    sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    L.femb200_ctx_set_stream(holder.ctx, C.c_void_p(sa.cuda_stream))
+    L.femb200_ctx_set_stream(holder_b.ctx, C.c_void_p(sb.cuda_stream))
+    L.femb200_ctx_set_concurrent(holder.ctx, 1)
+    L.femb200_ctx_set_concurrent(holder_b.ctx, 1)
+    pool = ThreadPoolExecutor(max_workers=1)
     desc = holder.make_desc(elemT, c)
+    px = D.PlannedExchange(iplan, dev)
 
     class View:
         def __init__(self, h):
@@ -257,72 +279,138 @@ def run_multi_gpu(args, rank, world, local_rank):
         def nnz(self):
             return L.femb200_nnz(self.h)
 
-    def new_assembler(mask):
+    def new_assembler(mask, ctx=None):
         h = C.c_void_p()
-        assert L.femb200_assembler_create(holder.ctx, C.c_void_p(d_nodes.data_ptr()), nodes.shape[0], 3, 1, C.byref(h)) == 0
+        assert L.femb200_assembler_create(ctx or holder.ctx, C.c_void_p(d_nodes.data_ptr()), nodes.shape[0], 3, 1, C.byref(h)) == 0
         L.femb200_assembler_set_node_mask_device(h, C.c_void_p(mask.data_ptr()))
         return h
 
-    def step():
+    def assemble_outgoing():
+        # interface rows to send: own elements touching foreign nodes, rows of foreign nodes only
+        torch.cuda.set_device(local_rank)
+        hb = new_assembler(m_send, holder_b.ctx)
+        rc = L.femb200_add_isoparametric(hb, C.byref(desc), C.c_void_p(d_out.data_ptr()), 0, 1, out_conn.shape[0])
+        assert rc == 0, rc
+        return hb
+
+    sub_t = {}
+
+    def step_exchange_diag():
+        """FEMB200_BENCH_SUBSTEPS=1: the same step serialised, host clock per sub-step (diagnostics only)."""
+        def mark(name, t0):
+            torch.cuda.synchronize()
+            sub_t[name] = sub_t.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+            return time.perf_counter()
+        t0 = time.perf_counter()
+        ha = new_assembler(m_own)
+        rc = L.femb200_add_isoparametric_halo(ha, C.byref(desc), C.c_void_p(d_conn.data_ptr()), 0, 1, my.shape[0], nhalo)
+        t0 = mark("owned_block", t0)
+        hb = assemble_outgoing()
+        t0 = mark("outgoing_rows", t0)
+        be_a, be_b = D.Femb200Backend(pkg, View(ha), dev), D.Femb200Backend(pkg, View(hb), dev)
+        tt = [t0]
+
+        def ap():
+            s0.wait_stream(sb)
+            tt[0] = mark("pack", tt[0])
+
+        def ac():
+            tt[0] = mark("all_to_all", tt[0])
+            sa.wait_stream(s0)
+        sent = px.run(be_a, be_b, dist, after_pack=ap, after_collective=ac)
+        s0.wait_stream(sa)
+        t0 = mark("add", tt[0])
+        nnz = L.femb200_nnz(ha)
+        L.femb200_assembler_destroy(ha)
+        L.femb200_assembler_destroy(hb)
+        mark("destroy", t0)
+        return sent, nnz
+
+    def step_exchange():
+        if os.environ.get("FEMB200_BENCH_SUBSTEPS"):
+            return step_exchange_diag()
+        fut = pool.submit(assemble_outgoing)
         # owned row block: own elements + pattern-only halo, rows of owned nodes only
         ha = new_assembler(m_own)
         rc = L.femb200_add_isoparametric_halo(ha, C.byref(desc), C.c_void_p(d_conn.data_ptr()), 0, 1, my.shape[0], nhalo)
         assert rc == 0, rc
-        # interface rows to send: own elements touching foreign nodes, rows of foreign nodes only
-        hb = new_assembler(m_send)
-        rc = L.femb200_add_isoparametric(hb, C.byref(desc), C.c_void_p(d_out.data_ptr()), 0, 1, out_conn.shape[0])
-        assert rc == 0, rc
-        sent = D.exchange_into_owned(D.Femb200Backend(pkg, View(ha), dev), D.Femb200Backend(pkg, View(hb), dev), plan, dev, dist,
-                                     timings=step.timings)
+        hb = fut.result()
+        # both calls have synchronised their streams; pack on sb -> all-to-all on s0 -> adds on sa -> s0 waits for sa
+        sent = px.run(D.Femb200Backend(pkg, View(ha), dev), D.Femb200Backend(pkg, View(hb), dev), dist,
+                      after_pack=lambda: s0.wait_stream(sb), after_collective=lambda: sa.wait_stream(s0))
+        s0.wait_stream(sa)
         nnz = L.femb200_nnz(ha)
-        L.femb200_assembler_destroy(ha)
+        L.femb200_assembler_destroy(ha)      # synchronises its stream: the exchange is complete when the step returns
         L.femb200_assembler_destroy(hb)
         return sent, nnz
 
-    step.timings = {} if os.environ.get("FEMB200_BENCH_SUBSTEPS") else None
+    def step_owner_computes():
+        ha = new_assembler(m_own)
+        rc = L.femb200_add_isoparametric(ha, C.byref(desc), C.c_void_p(d_ghost.data_ptr()), 0, 1, ghost.shape[0])
+        assert rc == 0, rc
+        nnz = L.femb200_nnz(ha)
+        L.femb200_assembler_destroy(ha)
+        return 0, nnz
+
     warmup = max(args.warmup, 3)
-    for _ in range(warmup):
-        step()
-        flush.fill_(1)
-    torch.cuda.synchronize()
-    dist.barrier()
-    if step.timings is not None:
-        step.timings.clear()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = L.femb200_kernel_launches(holder.ctx)
-    times = []
-    sent = nnz = 0
-    for _ in range(args.steps):
-        flush.fill_(1)
+
+    def timed(step):
+        for _ in range(warmup):
+            step()
+            flush.fill_(1)
         torch.cuda.synchronize()
         dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        sent, nnz = step()
-        e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    launches = L.femb200_kernel_launches(holder.ctx) - launches0
-    clocks = sampler.finish()
-    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot = torch.tensor([float(sent), float(nnz)], dtype=torch.float64, device=dev)
-    dist.all_reduce(tot)
-    ms = float(t.item())
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = L.femb200_kernel_launches(holder.ctx)
+        times = []
+        sent = nnz = 0
+        sub_t.clear()
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sent, nnz = step()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        launches = L.femb200_kernel_launches(holder.ctx) - launches0
+        clocks = sampler.finish()
+        t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([float(sent), float(nnz)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        return float(t.item()), tot[0].item(), tot[1].item(), int(launches), clocks
+
+    ms_x, sent_b, nnz_x, launches_x, _ = timed(step_exchange)
+    sub_x = dict(sub_t)
+    mism = torch.tensor([float(px.mismatches())], dtype=torch.float64, device=dev)
+    dist.all_reduce(mism)
+    ms, _, nnz_t, launches, clocks = timed(step_owner_computes)
+    halo_tot = torch.tensor([float(nhalo)], dtype=torch.float64, device=dev)
+    dist.all_reduce(halo_tot)
     if rank == 0:
         value = ne_total / (ms * 1e-3)
         line = {"metric": "K assembly elements/s", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"Tetra4 BCC box {N * world}x{N}x{N}: {ne_total} elements / {nodes.shape[0] * 3} dofs ({world} x config 1), Isotropic(E=200e9, nu=0.3).Solid3D",
                            "l2": "flushed between timed steps (256 MiB write)", "inputs": "nodes f64 + int32 connectivity chunk resident in HBM",
-                           "multi_gpu": "contiguous cell-major element chunks; lowest-rank node ownership; per rank: owned row block assembled with pattern-only halo elements + interface rows assembled separately; NCCL all-to-all of the interface rows; in-place add in ascending source rank"},
-                "dofs_per_s": value * nodes.shape[0] * 3 / ne_total, "interface_bytes_sent_total": tot[0].item(), "nnz_total": tot[1].item(),
+                           "multi_gpu": "contiguous cell-major element chunks, one per GPU; a node (row block) belongs to the lowest rank touching it; "
+                                        "owner computes: every rank assembles its own elements plus the halo elements touching its rows "
+                                        "(redundant O(surface) work, ascending global element order => rows bit-identical to 1 GPU), no data-path collective; "
+                                        "the NCCL row exchange of partial interface rows is timed alongside (key 'row_exchange')"},
+                "dofs_per_s": value * nodes.shape[0] * 3 / ne_total, "nnz_total": nnz_t, "redundant_halo_elements_total": halo_tot.item(),
+                "row_exchange": {"value": ne_total / (ms_x * 1e-3), "unit": "elements/s", "ms_per_step": ms_x, "gpu_launches": launches_x,
+                                 "interface_bytes_sent_total": sent_b, "nnz_total": nnz_x, "plan_mismatches": mism.item(),
+                                 "note": "north-star scheme: owned rows from [own ; halo (pattern only)], interface rows from the own elements touching foreign "
+                                         "nodes (second context, concurrent), ONE NCCL all-to-all with plan-time sizes, in-place add in ascending source rank"},
                 "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "note": "multi-GPU result stays distributed on the devices (row blocks); host-buffer e2e is reported at N=1"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None}
-        if step.timings is not None:
-            line["exchange_substeps_ms_rank0"] = {k: v / args.steps for k, v in step.timings.items()}
+                "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None}
+        if sub_x:
+            line["row_exchange"]["substeps_ms_rank0_serialised"] = {k: v / args.steps for k, v in sub_x.items()}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
@@ -348,6 +436,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # the version banner goes to stdout; the contract is ONE JSON line
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))

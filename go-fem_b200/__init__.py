@@ -53,6 +53,7 @@ def lib():
     L.femb200_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.femb200_ctx_destroy.argtypes = [vp]
     L.femb200_ctx_set_stream.argtypes = [vp, vp]
+    L.femb200_ctx_set_concurrent.argtypes = [vp, C.c_int32]
     L.femb200_last_cuda_error.argtypes = [vp]
     L.femb200_last_cuda_error.restype = C.c_char_p
     L.femb200_assembler_create.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -71,6 +72,8 @@ def lib():
     L.femb200_csr_keep_rows_device.argtypes = [vp, vp]
     L.femb200_assembler_set_node_mask_device.argtypes = [vp, vp]
     L.femb200_csr_add_entries_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    L.femb200_csr_pack_rows_async.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
+    L.femb200_csr_add_entries_async.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
     L.femb200_add_isoparametric_halo.argtypes = [vp, C.POINTER(ElemDesc), vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64]
     L.femb200_last_slot_map.argtypes = [vp, _i64p]
     L.femb200_isoparametric_strains.argtypes = [vp, C.POINTER(ElemDesc), vp, C.c_int32, C.c_int32, C.c_int64, _dp, _dp]

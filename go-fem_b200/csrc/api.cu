@@ -64,6 +64,12 @@ int femb200_ctx_set_stream(femb200_ctx *ctx, void *s) {
   return 0;
 }
 
+int femb200_ctx_set_concurrent(femb200_ctx *ctx, int32_t on) {
+  if (!ctx) return FEMB200_ERR_BAD_ARG;
+  ctx->concurrent = on != 0;
+  return 0;
+}
+
 const char *femb200_last_cuda_error(const femb200_ctx *ctx) { return ctx ? ctx->last_cuda_error.c_str() : "no context"; }
 int64_t femb200_kernel_launches(const femb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int femb200_sync(femb200_ctx *ctx) {
@@ -357,6 +363,22 @@ int femb200_csr_add_entries_device(femb200_assembler *ga, int64_t n_rows, const 
   if (!ga || n_rows < 0 || (n_rows > 0 && (!rows || !indptr))) return FEMB200_ERR_BAD_ARG;
   FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
   return csr_add_entries(ga, n_rows, rows, indptr, indices, values);
+}
+
+int femb200_csr_pack_rows_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *out_indptr,
+                                int32_t *out_indices, double *out_values, uint64_t *mismatch) {
+  if (!ga || n_rows < 0 || (n_rows > 0 && (!rows || !out_indptr))) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
+  if (n_rows > 0 && ga->K.nnz == 0) return FEMB200_ERR_PATTERN;
+  return csr_pack_rows_async(ga, n_rows, rows, out_indptr, out_indices, out_values, (unsigned long long *)mismatch);
+}
+
+int femb200_csr_add_entries_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr,
+                                  const int32_t *indices, const double *values, uint64_t *mismatch) {
+  if (!ga || n_rows < 0 || (n_rows > 0 && (!rows || !indptr))) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
+  if (n_rows > 0 && ga->K.nnz == 0) return FEMB200_ERR_PATTERN;
+  return csr_add_entries_async(ga, n_rows, rows, indptr, indices, values, (unsigned long long *)mismatch);
 }
 
 int femb200_assembler_set_node_mask_device(femb200_assembler *ga, const uint8_t *node_mask) {

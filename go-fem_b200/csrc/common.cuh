@@ -59,6 +59,7 @@ struct femb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  bool concurrent = false;                  // other contexts may run calls on this device at the same time
   cudaMemPool_t pool = nullptr;
   int sm_count = 148;
   size_t smem_optin = 0;
@@ -146,6 +147,10 @@ int csr_keep_rows(femb200_assembler *ga, const uint8_t *keep);
 int csr_add_entries(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
                     const double *values);
 int csr_matvec(femb200_assembler *ga, const double *d_x, double *d_y);
+int csr_pack_rows_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *out_indptr, int32_t *out_indices,
+                        double *out_values, unsigned long long *mismatch);
+int csr_add_entries_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
+                          const double *values, unsigned long long *mismatch);
 int strains_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32,
                   int64_t n_elem, const int32_t *d_dofmap, const double *d_u, double *d_strains);
 int narrow_and_validate_conn(femb200_assembler *ga, const void *d_conn_in, bool is64, int64_t n, int nn,

@@ -170,6 +170,66 @@ int csr_add_entries(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, 
   return 0;
 }
 
+// ---- planned interface exchange (distributed.py): asynchronous pack and add, no host synchronisation ----------
+// 8 lanes per row: copies row rows[w] of K into the packed arrays at the offsets the partition plan fixed; a row
+// whose length differs from the plan bumps *mismatch and is truncated / zero padded.
+__global__ void k_pack_rows(int64_t n_rows, const int64_t *__restrict__ rows, const int64_t *__restrict__ optr,
+                            const int64_t *__restrict__ kptr, const int32_t *__restrict__ kidx, const double *__restrict__ kval,
+                            int32_t *__restrict__ oidx, double *__restrict__ oval, unsigned long long *mismatch) {
+  const int l = threadIdx.x & 7;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (w >= n_rows) return;
+  const int64_t r = rows[w];
+  const int64_t s = kptr[r], m = kptr[r + 1] - s, d = optr[w], cap = optr[w + 1] - d;
+  if (m != cap && l == 0 && mismatch) atomicAdd(mismatch, 1ull);
+  for (int64_t k = l; k < cap; k += 8) {
+    oidx[d + k] = k < m ? kidx[s + k] : -1;
+    oval[d + k] = k < m ? kval[s + k] : 0.0;
+  }
+}
+
+__global__ void k_add_entries_async(int64_t n_rows, const int64_t *__restrict__ rows, const int64_t *__restrict__ ptr0,
+                                    const int32_t *__restrict__ idx, const double *__restrict__ val, const int64_t *__restrict__ kptr,
+                                    const int32_t *__restrict__ kidx, double *__restrict__ kval, unsigned long long *mismatch) {
+  const int l = threadIdx.x & 7;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (w >= n_rows) return;
+  const int64_t r = rows[w];
+  const int64_t lo0 = kptr[r], hi0 = kptr[r + 1];
+  for (int64_t k = ptr0[w] + l; k < ptr0[w + 1]; k += 8) {
+    const int32_t c = idx[k];
+    int64_t lo = lo0, hi = hi0;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (kidx[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    if (lo < hi0 && kidx[lo] == c) kval[lo] += val[k];   // (row, col) unique within a piece: no two lanes share a slot
+    else if (mismatch) atomicAdd(mismatch, 1ull);
+  }
+}
+
+int csr_pack_rows_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *out_indptr, int32_t *out_indices,
+                        double *out_values, unsigned long long *mismatch) {
+  femb200_ctx *ctx = ga->ctx;
+  if (n_rows == 0) return 0;
+  k_pack_rows<<<grid_for(n_rows * 8, 256), 256, 0, ctx->stream>>>(n_rows, rows, out_indptr, ga->K.indptr, ga->K.indices, ga->K.values,
+                                                                   out_indices, out_values, mismatch);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+int csr_add_entries_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
+                          const double *values, unsigned long long *mismatch) {
+  femb200_ctx *ctx = ga->ctx;
+  if (n_rows == 0) return 0;
+  k_add_entries_async<<<grid_for(n_rows * 8, 256), 256, 0, ctx->stream>>>(n_rows, rows, indptr, indices, values, ga->K.indptr, ga->K.indices,
+                                                                           ga->K.values, mismatch);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
 __global__ void k_keep_lens(int64_t n, const int64_t *__restrict__ ptr, const uint8_t *__restrict__ keep, int64_t *__restrict__ len) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n) return;

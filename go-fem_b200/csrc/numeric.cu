@@ -384,7 +384,6 @@ k_numeric_rows(const NumArgs a) {
 //                 a repeated node are flagged (degen[e]) for the ordered slow path of the row kernel.
 //  k_rows      -- deterministic row reduction fused with the B^T C B products (see the comment on the kernel).
 // =====================================================================================================
-__constant__ double c_C[kMaxDimC * kMaxDimC]; // constitutive matrix of the running call (row-major dimC x dimC)
 
 template <int BKIND, int D, int NN> struct Stag {
   using B = BT<BKIND, D>;
@@ -480,6 +479,7 @@ struct RowArgs {
   int64_t ninc;               // n_elem * nn (length of n2e_t)
   int nqp;
   int dbg;                    // FEMB200_DBG experiment bits (0 in production)
+  double C[kMaxDimC * kMaxDimC]; // constitutive matrix (row-major dimC x dimC): kernel-parameter space = constant bank
 };
 
 // ---- the node-row kernel (default) ----------------------------------------------------------------------
@@ -506,12 +506,12 @@ template <int BKIND, int D, int I_, int M_> struct KRow { // row k of B with sel
 };
 
 template <int BKIND, int D, int I_, int M_>
-__device__ __forceinline__ void e_row_add(double u, double (&E)[BT<BKIND, D>::DIMC]) {
+__device__ __forceinline__ void e_row_add(const RowArgs &a, double u, double (&E)[BT<BKIND, D>::DIMC]) {
   constexpr int KR = KRow<BKIND, D, I_, M_>::value();
   constexpr int DIMC = BT<BKIND, D>::DIMC;
   if constexpr (KR >= 0) {
 #pragma unroll
-    for (int c = 0; c < DIMC; ++c) E[c] = fma(u, c_C[KR * DIMC + c], E[c]);
+    for (int c = 0; c < DIMC; ++c) E[c] = fma(u, a.C[KR * DIMC + c], E[c]);
   }
 }
 
@@ -656,9 +656,9 @@ k_noderows(const RowArgs a) {
       double E[DIMC];
 #pragma unroll
       for (int c = 0; c < DIMC; ++c) E[c] = 0.0;
-      e_row_add<BKIND, D, I_, 0>(u[0], E);
-      if constexpr (NV > 1) e_row_add<BKIND, D, I_, (NV > 1 ? 1 : 0)>(u[NV > 1 ? 1 : 0], E);
-      if constexpr (NV > 2) e_row_add<BKIND, D, I_, (NV > 2 ? 2 : 0)>(u[NV > 2 ? 2 : 0], E);
+      e_row_add<BKIND, D, I_, 0>(a, u[0], E);
+      if constexpr (NV > 1) e_row_add<BKIND, D, I_, (NV > 1 ? 1 : 0)>(a, u[NV > 1 ? 1 : 0], E);
+      if constexpr (NV > 2) e_row_add<BKIND, D, I_, (NV > 2 ? 2 : 0)>(a, u[NV > 2 ? 2 : 0], E);
 #pragma unroll
       for (int s = 0; s < NB; ++s) {
         if (NN % G == 0 || g + G * s < NN) {
@@ -786,7 +786,6 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
     const size_t smem_min = (size_t)sym->max_rowlen * B::NDN * B::NDN * sizeof(double) * ((32 / G2) | 1);
     if (smem_min > ctx->smem_optin) return -2; // caller falls back to global accumulators
   }
-  FEMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_C, h_tab, sizeof(double) * sh.dimC * sh.dimC, 0, cudaMemcpyHostToDevice, ctx->stream));
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
   double *stag = nullptr;
   uint8_t *degen = nullptr;
@@ -804,6 +803,7 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
   a.stag = stag; a.degen = degen; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
   a.dbg = getenv("FEMB200_DBG") ? atoi(getenv("FEMB200_DBG")) : 0;
+  for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
   rc = -2;
   if (gsel == G0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym->max_rowlen);
   if (rc == -2 && gsel <= G1) rc = launch_noderows<D, NN, BKIND, G1>(ctx, a, sym->max_rowlen);
@@ -907,7 +907,7 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
                   const int32_t *conn32, int64_t n_elem, SymbolicResult *sym) {
   femb200_ctx *ctx = ga->ctx;
   if (!numeric_supported(sh)) return FEMB200_ERR_UNSUPPORTED;
-  const bool tab_const = tab_doubles <= kTabDoubles;
+  const bool tab_const = tab_doubles <= kTabDoubles && !ctx->concurrent; // __constant__ tables are per device: one call at a time
   if (tab_const)
     FEMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_tab, h_tab, sizeof(double) * tab_doubles, 0, cudaMemcpyHostToDevice, ctx->stream));
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);

@@ -99,6 +99,112 @@ class ExchangePlan:
         return np.concatenate([own, conn[self.halo_elems]], axis=0), int(self.halo_elems.size)
 
 
+# ----------------------------------------------------------------------------- planned exchange (host, once per mesh)
+def interface_block_rows(n_nodes, conn, bounds, owner, p):
+    """Interface pattern of sender p, exact: for every node J that p's elements touch and another rank owns, the
+    number of distinct column nodes p's elements couple it to.  Returns (nodes ascending, counts)."""
+    own = conn[bounds[p]:bounds[p + 1]]
+    foreign = owner[own] != p
+    ei, ai = np.nonzero(foreign)
+    if ei.size == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    rown = own[ei, ai].astype(np.int64)                                    # foreign row node of the pair
+    keys = np.unique((rown[:, None] * n_nodes + own[ei].astype(np.int64)).ravel())
+    rn, cnt = np.unique(keys // n_nodes, return_counts=True)
+    return rn, cnt.astype(np.int64)
+
+
+class InterfacePlan:
+    """Everything the per-assembly exchange needs, fixed by (mesh, partition): for every peer q the scalar rows this
+    rank sends to q with their exact lengths, and for every source p the rows it receives, as packed-CSR offsets.
+    One payload per peer: [values f64 x nnz | indices int32 x nnz]; the split sizes are known on both sides, so the
+    exchange is ONE all-to-all with no size round trip.  `nu` = scalar dofs per node block (identity dof map)."""
+
+    def __init__(self, xplan, n_nodes, conn, bounds, nu, dist=None):
+        self.world, self.rank, self.nu = xplan.world, xplan.rank, nu
+        rn, cnt = interface_block_rows(n_nodes, conn, bounds, xplan.owner, self.rank)
+        own_of = xplan.owner[rn] if rn.size else np.zeros(0, dtype=np.int32)
+        self.send = []                                                     # per peer: (rows int64, indptr int64)
+        for q in range(self.world):
+            sel = own_of == q
+            self.send.append(self._rows_ptr(rn[sel], cnt[sel], nu))
+        mine = [(r, p) for (r, p) in self.send]
+        if dist is not None and self.world > 1:
+            allp = [None] * self.world
+            dist.all_gather_object(allp, mine)
+            self.recv = [allp[p][self.rank] for p in range(self.world)]
+        else:                                                              # single process (tests): derive the peers' plans locally
+            self.recv = []
+            for p in range(self.world):
+                rnp, cntp = interface_block_rows(n_nodes, conn, bounds, xplan.owner, p)
+                sel = xplan.owner[rnp] == self.rank if rnp.size else np.zeros(0, dtype=bool)
+                self.recv.append(self._rows_ptr(rnp[sel], cntp[sel], nu) if p != self.rank else self._rows_ptr(rnp[:0], cntp[:0], nu))
+        self.send_nnz = [int(p[-1]) for _, p in self.send]
+        self.recv_nnz = [int(p[-1]) for _, p in self.recv]
+        self.send_bytes = [(12 * n + 15) // 16 * 16 for n in self.send_nnz]   # 16-byte aligned payloads
+        self.recv_bytes = [(12 * n + 15) // 16 * 16 for n in self.recv_nnz]
+
+    @staticmethod
+    def _rows_ptr(nodes_, cnt, nu):
+        rows = (nodes_[:, None] * nu + np.arange(nu, dtype=np.int64)[None, :]).ravel()
+        lens = np.repeat(cnt * nu, nu)
+        ptr = np.zeros(rows.size + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        return rows.astype(np.int64), ptr
+
+
+class PlannedExchange:
+    """Per-rank state of the planned exchange (torch tensors on `device`); pack / add are delegated to the local
+    backends (the C ABI kernels on the GPU, numpy in the gloo tests)."""
+
+    def __init__(self, iplan, device):
+        import torch
+        self.p, self.device = iplan, device
+        t = lambda a: torch.as_tensor(a, device=device)
+        self.send_rows = [t(r) for r, _ in iplan.send]
+        self.send_ptr = [t(p) for _, p in iplan.send]
+        self.recv_rows = [t(r) for r, _ in iplan.recv]
+        self.recv_ptr = [t(p) for _, p in iplan.recv]
+        self.sendbuf = torch.zeros(max(sum(iplan.send_bytes), 16), dtype=torch.uint8, device=device)
+        self.recvbuf = torch.zeros(max(sum(iplan.recv_bytes), 16), dtype=torch.uint8, device=device)
+        self.mismatch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.soff = np.concatenate([[0], np.cumsum(iplan.send_bytes)]).astype(np.int64)
+        self.roff = np.concatenate([[0], np.cumsum(iplan.recv_bytes)]).astype(np.int64)
+
+    @staticmethod
+    def _views(buf, off, n):
+        import torch
+        val = buf[off:off + 8 * n].view(torch.float64)
+        idx = buf[off + 8 * n:off + 12 * n].view(torch.int32)
+        return idx, val
+
+    def run(self, owned, outgoing, dist, after_pack=None, after_collective=None):
+        """outgoing (backend holding the interface rows) -> peers -> added into owned, ascending source rank.
+        On the GPU everything is only enqueued (pack on outgoing's stream, the collective on torch's current stream,
+        the adds on owned's stream); the two hooks let the caller order those streams (stream.wait_stream)."""
+        p = self.p
+        for q in range(p.world):
+            if q == p.rank or self.send_rows[q].numel() == 0:
+                continue
+            idx, val = self._views(self.sendbuf, int(self.soff[q]), p.send_nnz[q])
+            outgoing.pack_rows_into(self.send_rows[q], self.send_ptr[q], idx, val, self.mismatch)
+        if after_pack is not None:
+            after_pack()
+        dist.all_to_all_single(self.recvbuf[:int(self.roff[-1])], self.sendbuf[:int(self.soff[-1])],
+                               output_split_sizes=[int(b) for b in p.recv_bytes], input_split_sizes=[int(b) for b in p.send_bytes])
+        if after_collective is not None:
+            after_collective()
+        for src in range(p.world):                   # fixed order: ascending source rank => bit-reproducible
+            if src == p.rank or self.recv_rows[src].numel() == 0:
+                continue
+            idx, val = self._views(self.recvbuf, int(self.roff[src]), p.recv_nnz[src])
+            owned.add_entries_from(self.recv_rows[src], self.recv_ptr[src], idx, val, self.mismatch)
+        return int(sum(12 * n for n in p.send_nnz))
+
+    def mismatches(self):
+        return int(self.mismatch.item())
+
+
 # ----------------------------------------------------------------------------- ragged CSR pieces (torch tensors)
 def gather_rows(indptr, indices, values, rows):
     """Packs the given (ascending) rows of a CSR held in torch tensors: returns (lens, indices, values)."""
@@ -296,6 +402,23 @@ class Femb200Backend(LocalBackend):
             raise RuntimeError(f"femb200_csr_add_entries_device -> {rc}")
         return rc == 0
 
+    def _h(self):
+        return self.raw.h
+
+    def pack_rows_into(self, rows, ptr, idx, val, mismatch):
+        c = self.C.c_void_p
+        rc = self.pkg.lib().femb200_csr_pack_rows_async(self._h(), rows.numel(), c(rows.data_ptr()), c(ptr.data_ptr()), c(idx.data_ptr()),
+                                                        c(val.data_ptr()), c(mismatch.data_ptr()))
+        if rc:
+            raise RuntimeError(f"femb200_csr_pack_rows_async -> {rc}")
+
+    def add_entries_from(self, rows, ptr, idx, val, mismatch):
+        c = self.C.c_void_p
+        rc = self.pkg.lib().femb200_csr_add_entries_async(self._h(), rows.numel(), c(rows.data_ptr()), c(ptr.data_ptr()), c(idx.data_ptr()),
+                                                          c(val.data_ptr()), c(mismatch.data_ptr()))
+        if rc:
+            raise RuntimeError(f"femb200_csr_add_entries_async -> {rc}")
+
 
 class NumpyBackend(LocalBackend):
     """CPU stand-in used by the gloo tests: holds a canonical CSR in numpy, merges like the device kernels
@@ -328,6 +451,25 @@ class NumpyBackend(LocalBackend):
             slots[ptr[w]:ptr[w + 1]] = pos
         self.values[slots] += val
         return True
+
+    def pack_rows_into(self, rows, ptr, idx, val, mismatch):
+        rows, ptr, oi, ov = rows.numpy(), ptr.numpy(), idx.numpy(), val.numpy()
+        for w, r in enumerate(rows):
+            lo, hi = self.indptr[r], self.indptr[r + 1]
+            if hi - lo != ptr[w + 1] - ptr[w]:
+                mismatch += 1
+                continue
+            oi[ptr[w]:ptr[w + 1]] = self.indices[lo:hi]
+            ov[ptr[w]:ptr[w + 1]] = self.values[lo:hi]
+
+    def add_entries_from(self, rows, ptr, idx, val, mismatch):
+        if not self.add_entries(rows, ptr, idx, val):
+            mismatch += 1
+
+    def restrict_rows(self, node_mask, mdpn):
+        """Keeps only the rows of the masked nodes (what the device assembler does with a node mask)."""
+        import torch
+        self.keep_rows(torch.from_numpy(np.repeat(node_mask.astype(np.uint8), mdpn)))
 
     def accumulate_rows(self, rows, indptr0, indices, values):
         rows, ptr, idx, val = rows.numpy(), indptr0.numpy(), indices.numpy(), values.numpy()

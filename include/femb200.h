@@ -80,6 +80,11 @@ int femb200_ctx_create(int device, femb200_ctx **out);
 void femb200_ctx_destroy(femb200_ctx *ctx);
 /* Runs on an externally owned stream (cudaStream_t as void*), e.g. torch's current stream. */
 int femb200_ctx_set_stream(femb200_ctx *ctx, void *cuda_stream);
+/* Several contexts of ONE device may run add calls at the same time (one host thread and one stream each) once
+ * every one of them has been switched to concurrent mode: the per-call element tables then live in global memory
+ * instead of the device-wide __constant__ bank.  (A rank of the multi-GPU path assembles its owned row block and
+ * its outgoing interface rows this way, the small second call filling the gaps of the first.) */
+int femb200_ctx_set_concurrent(femb200_ctx *ctx, int32_t on);
 const char *femb200_last_cuda_error(const femb200_ctx *ctx);
 
 /* fem.NewGeneralAssembler(nodes []r3.Vec, modelDofs) (assembler.go:21-28).
@@ -142,6 +147,16 @@ int femb200_assembler_set_node_mask_device(femb200_assembler *ga, const uint8_t 
  * FEMB200_ERR_PATTERN if an entry is missing (checked in a first pass: K is untouched on failure). */
 int femb200_csr_add_entries_device(femb200_assembler *ga, int64_t n_rows, const int64_t *rows,
                                    const int64_t *indptr, const int32_t *indices, const double *values);
+/* Planned interface exchange (no reference counterpart; go-fem_b200/distributed.py): the partition plan fixes, once
+ * per mesh, which rows every rank sends to every owner and how long they are, so the per-assembly exchange is
+ * pack -> ONE collective -> add with no size round trip and no host synchronisation.  Both calls only enqueue
+ * work on the context stream; *mismatch (device uint64, may be NULL) counts rows / entries that contradict the plan.
+ *  pack: entries of row rows[w] of K -> out_indices / out_values [out_indptr[w], out_indptr[w+1])
+ *  add : K[rows[w], indices[k]] += values[k], k in [indptr[w], indptr[w+1]); one call per source rank, ascending. */
+int femb200_csr_pack_rows_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *out_indptr,
+                                int32_t *out_indices, double *out_values, uint64_t *mismatch);
+int femb200_csr_add_entries_async(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr,
+                                  const int32_t *indices, const double *values, uint64_t *mismatch);
 /* Drops every row whose keep[row] == 0 (device byte mask, one per scalar row): after sending the rows it
  * does not own, a rank keeps exactly its row block of the distributed K. */
 int femb200_csr_keep_rows_device(femb200_assembler *ga, const uint8_t *keep);

@@ -50,7 +50,17 @@ for name, size in cases:
         rc = raw2.add(desc, conn=own_conn[plan.send_elems])
         assert rc == 0, (rc, raw2.last_error())
         be = D.Femb200Backend(pkg, raw, dev)
-        sent = D.exchange_into_owned(be, D.Femb200Backend(pkg, raw2, dev), plan, dev, dist)
+        if os.environ.get("FEMB200_RAGGED_EXCHANGE"):
+            sent = D.exchange_into_owned(be, D.Femb200Backend(pkg, raw2, dev), plan, dev, dist)
+        else:
+            iplan = D.InterfacePlan(plan, nodes.shape[0], conn, bounds, mdpn, dist)
+            px = D.PlannedExchange(iplan, dev)
+            # the library's stream must be the stream NCCL is enqueued on
+            for r_ in (raw, raw2):
+                L.femb200_ctx_set_stream(r_.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            sent = px.run(be, D.Femb200Backend(pkg, raw2, dev), dist)
+            torch.cuda.synchronize()
+            assert px.mismatches() == 0, px.mismatches()
     ptr, idx, val = D.gather_distributed_csr(be, plan, dist, dev)
     if rank == 0:
         O = entry.load_oracle()
@@ -62,7 +72,22 @@ for name, size in cases:
         ok = pat and nerr <= 1e-12
         ok_all &= ok
         print(f"[dist_check] {name} size={size} world={world} nelem={conn.shape[0]} nnz={rv.size} pattern_exact={pat} max_norm_err={nerr:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+    # owner-computes variant: own + halo elements, all numeric, ascending global element index; no collective
+    raw3 = pkg.RawAssembler(nodes, mdpn, device=lrank)
+    m_own3 = torch.as_tensor(plan.own_node_mask, device=dev)
+    L.femb200_assembler_set_node_mask_device(raw3.h, C.c_void_p(m_own3.data_ptr()))
+    gids = np.sort(np.concatenate([np.arange(bounds[rank], bounds[rank + 1]), plan.halo_elems]))
+    rc = raw3.add(desc, conn=conn[gids])
+    assert rc == 0, (rc, raw3.last_error())
+    ptr3, idx3, val3 = D.gather_distributed_csr(D.Femb200Backend(pkg, raw3, dev), plan, dist, dev)
+    if rank == 0:
+        pat3 = np.array_equal(ptr3, rp) and np.array_equal(idx3, ri)
+        nerr3 = (np.abs(val3 - rv) / np.maximum(np.maximum(np.abs(rv), ab), 1e-300)).max() if pat3 else float("inf")
+        ok3 = pat3 and nerr3 <= 1e-12
+        ok_all &= ok3
+        print(f"[dist_check] {name} owner-computes: pattern_exact={pat3} max_norm_err={nerr3:.2e} -> {'OK' if ok3 else 'FAIL'}", flush=True)
     raw.close()
+    raw3.close()
     if raw2 is not None:
         raw2.close()
     dist.barrier()

@@ -76,6 +76,84 @@ def test_row_block_exchange_gloo(world, kind, size, morton):
     assert all(p.exitcode == 0 for p in procs)
 
 
+def _worker_planned(rank, world, port, kind_name, size, q):
+    """Planned exchange (what bench.py runs on the GPUs): owned block assembled from [own ; halo(pattern only)], the
+    outgoing interface rows from the own elements touching foreign nodes, ONE all-to-all with plan-time sizes."""
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import torch
+        import torch.distributed as dist
+        import __graft_entry__ as entry
+        from conftest import KINDS
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        entry.load_package()
+        from importlib import import_module
+        D = import_module("gofem_b200.distributed")
+        M = import_module("gofem_b200.meshes")
+        O = entry.load_oracle()
+        nodes, conn = M.mesh_for(kind_name, size)
+        k = KINDS[kind_name]
+        conn = conn[D.morton_order(nodes, conn)]
+        Cm, bk = O.constitutive(k["mode"], 200e9, 0.3)
+        mdpn = bin(k["flags"]).count("1")
+        bounds = D.chunk_bounds(conn.shape[0], world)
+        plan = D.ExchangePlan(nodes.shape[0], conn, bounds, rank, mdpn)
+        iplan = D.InterfacePlan(plan, nodes.shape[0], conn, bounds, mdpn, dist)
+        local = D.InterfacePlan(plan, nodes.shape[0], conn, bounds, mdpn, None)     # peers' plans derived locally
+        for a, b in zip(iplan.recv, local.recv):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        own = conn[bounds[rank]:bounds[rank + 1]]
+        # owned block: values of the own elements, pattern of own + halo (the oracle assembles the halo with a zero material)
+        og = O.GeneralAssembler(nodes, k["flags"])
+        og.add_isoparametric(k["kind"], Cm, bk, own)
+        if plan.halo_elems.size:
+            og.add_isoparametric(k["kind"], Cm * 0.0, bk, conn[plan.halo_elems])
+        owned = D.NumpyBackend(*og.csr())
+        owned.restrict_rows(plan.own_node_mask, mdpn)
+        og2 = O.GeneralAssembler(nodes, k["flags"])
+        if plan.send_elems.size:
+            og2.add_isoparametric(k["kind"], Cm, bk, own[plan.send_elems])
+        outgoing = D.NumpyBackend(*og2.csr())
+        outgoing.restrict_rows(plan.send_node_mask, mdpn)
+        px = D.PlannedExchange(iplan, torch.device("cpu"))
+        sent = px.run(owned, outgoing, dist)
+        assert px.mismatches() == 0
+        tsent = torch.tensor([sent], dtype=torch.int64)
+        dist.all_reduce(tsent)
+        ptr, idx, val = D.gather_distributed_csr(owned, plan, dist, torch.device("cpu"))
+        if rank == 0:
+            full = O.GeneralAssembler(nodes, k["flags"])
+            full.add_isoparametric(k["kind"], Cm, bk, conn)
+            rp, ri, rv, ab = full.csr(with_absum=True)
+            ok = np.array_equal(ptr, rp) and np.array_equal(idx, ri) and bool(np.all(np.abs(val - rv) <= 1e-12 * np.maximum(np.abs(rv), ab)))
+            q.put((ok, int(tsent.item()), int(rv.size)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((False, traceback.format_exc(), 0))
+        raise
+
+
+@pytest.mark.parametrize("world,kind,size", [(2, "tetra4", 4), (3, "hexa8", 4)])
+def test_planned_exchange_gloo(world, kind, size):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 300) + world * 11 + size
+    procs = [ctx.Process(target=_worker_planned, args=(r, world, port, kind, size, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, sent, nnz = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=240)
+    assert ok is True, sent
+    assert sent > 0 and nnz > 0
+    assert all(p.exitcode == 0 for p in procs)
+
+
 def test_partition_helpers():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as entry
