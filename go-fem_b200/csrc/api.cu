@@ -45,6 +45,7 @@ void femb200_ctx_destroy(femb200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->cub_tmp) cudaFreeAsync(ctx->cub_tmp, ctx->stream);
+  scratch_release(ctx, true);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_err);
   cudaFree(ctx->d_scalars);
@@ -180,11 +181,13 @@ static int stage_conn(femb200_assembler *ga, const void *conn, bool is64, bool o
   femb200_ctx *ctx = ga->ctx;
   *staged = nullptr;
   int rc;
-  if ((rc = dev_alloc(ctx, conn32, (size_t)n))) return rc;
+  if ((rc = scratch_alloc(ctx, conn32, (size_t)n))) return rc;
   const void *d_in = conn;
   if (!on_device && n) {
     size_t bytes = (size_t)n * (is64 ? 8 : 4);
-    FEMB_CUDA_OK(ctx, cudaMallocAsync(staged, bytes, ctx->pool, ctx->stream));
+    char *sb = nullptr;
+    if ((rc = scratch_alloc(ctx, &sb, bytes))) return rc;
+    *staged = sb;
     FEMB_CUDA_OK(ctx, cudaMemcpyAsync(*staged, conn, bytes, cudaMemcpyHostToDevice, ctx->stream));
     d_in = *staged;
   }
@@ -218,18 +221,14 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   void *staged = nullptr;
   double *d_tab = nullptr;
   SymbolicResult sym;
-  auto cleanup = [&]() {
-    dev_free(ctx, conn32);
-    if (staged) cudaFreeAsync(staged, st);
-    dev_free(ctx, d_tab);
-    dev_free(ctx, sym.blkcols);
-  };
+  ScratchScope scratch_scope(ctx); // conn32, staged, d_tab, symbolic / numeric temporaries: released on every return path
+  auto cleanup = [&]() {};
   auto drop_sym = [&]() {
     dev_free(ctx, sym.n2e_ptr); dev_free(ctx, sym.n2e_t); dev_free(ctx, sym.pos16); dev_free(ctx, sym.blkptr);
     dev_free(ctx, sym.csr.indptr); dev_free(ctx, sym.csr.indices); dev_free(ctx, sym.csr.values);
   };
   rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged);
-  if (!rc) rc = dev_alloc(ctx, &d_tab, blob.size());
+  if (!rc) rc = scratch_alloc(ctx, &d_tab, blob.size());
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
@@ -430,6 +429,7 @@ int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc
   double *d_tab = nullptr, *d_u = nullptr, *d_s = nullptr;
   const int64_t ndof = ga->K.n_rows;
   const size_t ns = (size_t)n_elem * sh.nqp * sh.dimC;
+  ScratchScope scratch_scope(ctx); // conn32 + staged connectivity
   rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged);
   if (!rc) rc = dev_alloc(ctx, &d_tab, blob.size());
   if (!rc) rc = dev_alloc(ctx, &d_u, (size_t)ndof);
@@ -452,8 +452,7 @@ int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
   }
   if (!rc) rc = decode_error(ga);
-  dev_free(ctx, conn32); dev_free(ctx, d_tab); dev_free(ctx, d_u); dev_free(ctx, d_s); dev_free(ctx, d_dofmap);
-  if (staged) cudaFreeAsync(staged, st);
+  dev_free(ctx, d_tab); dev_free(ctx, d_u); dev_free(ctx, d_s); dev_free(ctx, d_dofmap);
   cudaStreamSynchronize(st);
   if (rc) ga->err_kind = rc;
   return rc;

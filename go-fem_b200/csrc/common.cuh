@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "../../include/femb200.h"
 
 namespace femb200 {
@@ -72,6 +73,11 @@ struct femb200_ctx {
   int64_t *h_scalars = nullptr;             // pinned host mirror
   unsigned long long *h_err = nullptr;      // pinned
   cudaEvent_t ev[12] = {};
+  // per-call scratch arena: temporaries of one add call are carved out of (normally) ONE persistent chunk, so a
+  // repeated assembly performs no allocation for them and the memory pool is not churned by multi-GB temporaries
+  struct ScratchChunk { char *p; size_t size; };
+  std::vector<ScratchChunk> scratch;
+  size_t scratch_off = 0, scratch_used = 0, scratch_hint = 0;
 };
 
 struct femb200_assembler {
@@ -111,6 +117,39 @@ template <class T> inline void dev_free(femb200_ctx *ctx, T *&p) {
   if (p) cudaFreeAsync((void *)p, ctx->stream);
   p = nullptr;
 }
+// bump allocation from the context's scratch arena (256-byte aligned); released as a whole by scratch_release
+template <class T> inline int scratch_alloc(femb200_ctx *ctx, T **p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+  if (ctx->scratch.empty() || ctx->scratch_off + bytes > ctx->scratch.back().size) {
+    size_t sz = bytes > ctx->scratch_hint ? bytes : ctx->scratch_hint;
+    if (!ctx->scratch.empty() && sz < ctx->scratch.back().size / 2) sz = ctx->scratch.back().size / 2; // geometric growth within a call
+    void *q = nullptr;
+    FEMB_CUDA_OK(ctx, cudaMallocAsync(&q, sz, ctx->pool, ctx->stream));
+    ctx->scratch.push_back({(char *)q, sz});
+    ctx->scratch_off = 0;
+  }
+  *p = reinterpret_cast<T *>(ctx->scratch.back().p + ctx->scratch_off);
+  ctx->scratch_off += bytes;
+  ctx->scratch_used += bytes;
+  return 0;
+}
+inline void scratch_release(femb200_ctx *ctx, bool drop_all = false) {
+  if (ctx->scratch.size() > 1 || drop_all) { // consolidate: the next call gets one chunk that fits everything
+    for (auto &c : ctx->scratch) cudaFreeAsync(c.p, ctx->stream);
+    ctx->scratch.clear();
+  }
+  if (ctx->scratch_used > ctx->scratch_hint) ctx->scratch_hint = ctx->scratch_used;
+  ctx->scratch_off = 0;
+  ctx->scratch_used = 0;
+}
+struct ScratchScope {
+  femb200_ctx *ctx;
+  explicit ScratchScope(femb200_ctx *c) : ctx(c) {}
+  ~ScratchScope() { scratch_release(ctx); }
+};
+
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // ---- phases (symbolic.cu / numeric.cu / csr_ops.cu) -------------------------------------------

@@ -789,9 +789,9 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
   double *stag = nullptr;
   uint8_t *degen = nullptr;
-  int rc = dev_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * S::REC);
+  int rc = scratch_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * S::REC);
   if (rc) return rc;
-  if ((rc = dev_alloc(ctx, &degen, (size_t)n_elem))) return rc;
+  if ((rc = scratch_alloc(ctx, &degen, (size_t)n_elem))) return rc;
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
   if (n_elem) {
     k_geometry<D, NN, BKIND, TAB_CONST><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, ga->d_nodes, conn32, stag, degen, ctx->d_err, d_tab,
@@ -810,8 +810,6 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   if (rc == -2) rc = launch_noderows<D, NN, BKIND, G2>(ctx, a, sym->max_rowlen);
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
   ga->split_numeric = true;
-  dev_free(ctx, stag);
-  dev_free(ctx, degen);
   return rc;
 }
 

@@ -373,7 +373,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
 
   // ---- node -> element adjacency -------------------------------------------------------------
   int32_t *cnt = nullptr;
-  if ((rc = dev_alloc(ctx, &cnt, 2 * (n_nodes + 1)))) return rc; // histogram | fill cursors
+  if ((rc = scratch_alloc(ctx, &cnt, 2 * (n_nodes + 1)))) return rc; // histogram | fill cursors
   int32_t *cursor = cnt + (n_nodes + 1);
   if ((rc = dev_alloc(ctx, &out->n2e_ptr, n_nodes + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->n2e_t, ninc))) return rc;
@@ -385,7 +385,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   size_t tmp1 = 0, tmp3 = 0, tmp4 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp1, cnt, out->n2e_ptr, (int)(n_nodes + 1), st);
   int64_t *rowlen = nullptr;
-  if ((rc = dev_alloc(ctx, &rowlen, n_nodes + 1))) return rc;
+  if ((rc = scratch_alloc(ctx, &rowlen, n_nodes + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->blkptr, n_nodes + 1))) return rc;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp3, rowlen, out->blkptr, (int)(n_nodes + 1), st);
   cub::DeviceReduce::Max(nullptr, tmp4, rowlen, ctx->d_scalars, (int)(n_nodes + 1), st);
@@ -403,7 +403,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
 
   // ---- node-block row pattern ----------------------------------------------------------------
   int32_t *tmpcols = nullptr;
-  if ((rc = dev_alloc(ctx, &tmpcols, ninc * nn))) return rc;
+  if ((rc = scratch_alloc(ctx, &tmpcols, ninc * nn))) return rc;
   if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn))) return rc;
   FEMB_CUDA_OK(ctx, cudaMemsetAsync(rowlen + n_nodes, 0, sizeof(int64_t), st));
   switch (nn) {
@@ -428,26 +428,24 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
   out->max_rowlen = (int)ctx->h_scalars[0];
   out->nblk = ctx->h_scalars[1];
-  dev_free(ctx, cnt);
-  dev_free(ctx, rowlen);
-  if (*ctx->h_err != kNoError) { dev_free(ctx, tmpcols); return -1; } // caller decodes the error word
-  if (out->max_rowlen > 65535) { dev_free(ctx, tmpcols); return FEMB200_ERR_TOO_LARGE; }
+  if (*ctx->h_err != kNoError) return -1; // caller decodes the error word
+  if (out->max_rowlen > 65535) return FEMB200_ERR_TOO_LARGE;
 
   // ---- scalar CSR pattern ----------------------------------------------------------------------
   const int nu = sh.nu;
   const int64_t nnz = (int64_t)nu * nu * out->nblk;
   const int64_t ndof = n_nodes * sh.mdpn;
-  if ((int64_t)out->max_rowlen * nu >= ((int64_t)1 << 31)) { dev_free(ctx, tmpcols); return FEMB200_ERR_TOO_LARGE; }
+  if ((int64_t)out->max_rowlen * nu >= ((int64_t)1 << 31)) return FEMB200_ERR_TOO_LARGE;
   out->csr.n_rows = ndof;
   out->csr.nnz = nnz;
   if ((rc = dev_alloc(ctx, &out->csr.indptr, ndof + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->csr.indices, nnz))) return rc;
   if ((rc = dev_alloc(ctx, &out->csr.values, nnz))) return rc;
-  if ((rc = dev_alloc(ctx, &out->blkcols, out->nblk))) return rc;
+  if ((rc = scratch_alloc(ctx, &out->blkcols, out->nblk))) return rc;
   unsigned umask = 0;
   for (int i = 0; i < nu; ++i) umask |= 1u << sh.umap[i];
   int *d_umap = nullptr;
-  if ((rc = dev_alloc(ctx, &d_umap, kMaxNdn))) return rc;
+  if ((rc = scratch_alloc(ctx, &d_umap, kMaxNdn))) return rc;
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_umap, sh.umap, sizeof(int) * kMaxNdn, cudaMemcpyHostToDevice, st));
   k_indptr<<<grid_for(ndof + 1, 256), 256, 0, st>>>(n_nodes, sh.mdpn, nu, umask, out->blkptr, out->csr.indptr);
   ctx->launches++;
@@ -456,8 +454,6 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
     ctx->launches++;
   }
   FEMB_CUDA_OK(ctx, cudaGetLastError());
-  dev_free(ctx, d_umap);
-  dev_free(ctx, tmpcols);
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
   return 0;
 }
