@@ -167,7 +167,6 @@ struct SymbolicResult {
   uint32_t *n2e_t = nullptr;
   uint16_t *pos16 = nullptr;
   int64_t *blkptr = nullptr;
-  int32_t *blkcols = nullptr;
   int64_t nblk = 0;
   int max_rowlen = 0;
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)

@@ -303,28 +303,34 @@ __global__ void k_indptr(int64_t n_nodes, int mdpn, int nu, unsigned umask, cons
   indptr[r] = (int64_t)nu * nu * blkptr[I] + (int64_t)before * rl * nu;
 }
 
-// one thread per node block g: finds its row by binary search on blkptr, compacts the column node and
-// writes the nu x nu scalar column indices (consecutive threads -> consecutive nu-int groups).
-__global__ void k_expand(int64_t n_nodes, int64_t nblk, int nn, int mdpn, int nu, const int *__restrict__ umap_packed,
-                         const int32_t *__restrict__ n2e_ptr, const int64_t *__restrict__ blkptr,
-                         const int32_t *__restrict__ tmpcols, int32_t *__restrict__ blkcols, int32_t *__restrict__ indices) {
-  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nblk) return;
-  int64_t lo = 0, hi = n_nodes; // largest I with blkptr[I] <= g
-  while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (blkptr[mid] <= g) lo = mid; else hi = mid;
-  }
-  const int64_t I = lo;
+// One warp per node row: expands the ascending column-node list of the row into the nu scalar CSR rows of the node.
+// The nu*nu*rl column indices of a node are contiguous in `indices` (scalar row ur at offset ur*rl*nu), so lane l
+// writes entries l, l+32, ...: fully coalesced 128-byte stores, the column nodes come from L1.
+template <int NU>
+__global__ void __launch_bounds__(256)
+k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ umap_packed, const int32_t *__restrict__ n2e_ptr,
+         const int64_t *__restrict__ blkptr, const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices) {
+  const int nu = NU > 0 ? NU : nu_rt;
+  const int lane = threadIdx.x & 31;
+  const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (I >= n_nodes) return;
   const int64_t b0 = blkptr[I];
-  const int p = (int)(g - b0);
-  const int64_t rl = blkptr[I + 1] - b0;
-  const int32_t J = tmpcols[(int64_t)nn * n2e_ptr[I] + p];
-  blkcols[g] = J;
-  const int64_t base = (int64_t)nu * nu * b0;
-  for (int ur = 0; ur < nu; ++ur)
-    for (int uc = 0; uc < nu; ++uc)
-      indices[base + (int64_t)ur * rl * nu + (int64_t)p * nu + uc] = J * mdpn + umap_packed[uc];
+  const int rl = (int)(blkptr[I + 1] - b0);
+  if (rl == 0) return;
+  const int32_t *cols = tmpcols + (int64_t)nn * n2e_ptr[I];
+  const int rowsz = rl * nu;
+  int um[NU > 0 ? NU : kMaxNdn];
+#pragma unroll
+  for (int u = 0; u < (NU > 0 ? NU : kMaxNdn); ++u) um[u] = u < nu ? umap_packed[u] : 0;
+  int32_t *out = indices + (int64_t)nu * nu * b0;
+  for (int idx = lane; idx < rowsz; idx += 32) {
+    const int p = idx / nu, uc = idx - p * nu;
+    int off = um[0];
+#pragma unroll
+    for (int u = 1; u < (NU > 0 ? NU : kMaxNdn); ++u) off = (uc == u) ? um[u] : off;
+    const int32_t c = cols[p] * mdpn + off;
+    for (int ur = 0; ur < nu; ++ur) out[(int64_t)ur * rowsz + idx] = c;
+  }
 }
 
 template <int NN>
@@ -441,7 +447,6 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   if ((rc = dev_alloc(ctx, &out->csr.indptr, ndof + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->csr.indices, nnz))) return rc;
   if ((rc = dev_alloc(ctx, &out->csr.values, nnz))) return rc;
-  if ((rc = scratch_alloc(ctx, &out->blkcols, out->nblk))) return rc;
   unsigned umask = 0;
   for (int i = 0; i < nu; ++i) umask |= 1u << sh.umap[i];
   int *d_umap = nullptr;
@@ -450,7 +455,13 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   k_indptr<<<grid_for(ndof + 1, 256), 256, 0, st>>>(n_nodes, sh.mdpn, nu, umask, out->blkptr, out->csr.indptr);
   ctx->launches++;
   if (out->nblk) {
-    k_expand<<<grid_for(out->nblk, 256), 256, 0, st>>>(n_nodes, out->nblk, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->blkcols, out->csr.indices);
+    const unsigned eg = grid_for(n_nodes * 32, 256);
+    switch (nu) {
+    case 1: k_expand<1><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
+    case 2: k_expand<2><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
+    case 3: k_expand<3><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
+    default: k_expand<0><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
+    }
     ctx->launches++;
   }
   FEMB_CUDA_OK(ctx, cudaGetLastError());
