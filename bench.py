@@ -235,26 +235,30 @@ def run_multi_gpu(args, rank, world, local_rank):
     bounds = D.chunk_bounds(ne_total, world)
     plan = D.ExchangePlan(nodes.shape[0], conn, bounds, rank, 3)
     iplan = D.InterfacePlan(plan, nodes.shape[0], conn, bounds, 3, dist)
-    lconn, nhalo = plan.local_connectivity(conn, bounds)
-    my = np.ascontiguousarray(lconn.astype(np.int32))
+    # rank-local node numbering (own + ghost nodes, ascending global id): every device array of a step is sized by
+    # the rank's share of the mesh; K rows are local, K column indices global
+    gids = np.sort(np.concatenate([np.arange(bounds[rank], bounds[rank + 1]), plan.halo_elems]))
+    ln = D.LocalNumbering(nodes, conn[gids])
+    lconn, nhalo = plan.local_connectivity(conn, bounds)            # [own ; halo] for the row-exchange variant
+    my = ln.conn(lconn)
     own_conn = conn[bounds[rank]:bounds[rank + 1]]
-    out_conn = np.ascontiguousarray(own_conn[plan.send_elems].astype(np.int32))
-    # owner-computes variant: own + halo elements in ascending GLOBAL element index (same summation order as 1 GPU)
-    gids = np.concatenate([np.arange(bounds[rank], bounds[rank + 1]), plan.halo_elems])
-    ghost = np.ascontiguousarray(conn[np.sort(gids)].astype(np.int32))
-    d_nodes = torch.from_numpy(nodes).to(dev)
+    out_conn = ln.conn(own_conn[plan.send_elems]) if plan.send_elems.size else np.zeros((0, 4), dtype=np.int32)
+    ghost = ln.conn(conn[gids])                                     # own + halo in ascending GLOBAL element index
+    n_local = ln.nodes.shape[0]
+    d_nodes = torch.from_numpy(ln.nodes).to(dev)
+    d_l2g = torch.from_numpy(ln.l2g.astype(np.int32)).to(dev)
     d_conn = torch.from_numpy(my).to(dev)
     d_ghost = torch.from_numpy(ghost).to(dev)
     d_out = torch.from_numpy(out_conn).to(dev) if out_conn.size else torch.zeros(4, dtype=torch.int32, device=dev)
-    m_own = torch.as_tensor(plan.own_node_mask, device=dev)
-    m_send = torch.as_tensor(plan.send_node_mask, device=dev)
+    m_own = torch.as_tensor(ln.node_mask(plan.own_node_mask), device=dev)
+    m_send = torch.as_tensor(ln.node_mask(plan.send_node_mask), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     elemT, c = pkg.elements.Tetra4(), pkg.solids.Isotropic(E_MOD, NU).Solid3D()
     # two library contexts per rank, one stream and one host thread each: the owned row block and the (small) set of
     # outgoing interface rows are assembled concurrently, the second call filling the gaps of the first
     from concurrent.futures import ThreadPoolExecutor
-    holder = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=nodes.shape[0])
-    holder_b = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=nodes.shape[0])
+    holder = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=n_local)
+    holder_b = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=n_local)
     L = pkg.lib()
     s0 = torch.cuda.current_stream()
     sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -264,7 +268,7 @@ def run_multi_gpu(args, rank, world, local_rank):
     L.femb200_ctx_set_concurrent(holder_b.ctx, 1)
     pool = ThreadPoolExecutor(max_workers=1)
     desc = holder.make_desc(elemT, c)
-    px = D.PlannedExchange(iplan, dev)
+    px = D.PlannedExchange(iplan, dev, local=ln)
 
     class View:
         def __init__(self, h):
@@ -281,8 +285,9 @@ def run_multi_gpu(args, rank, world, local_rank):
 
     def new_assembler(mask, ctx=None):
         h = C.c_void_p()
-        assert L.femb200_assembler_create(ctx or holder.ctx, C.c_void_p(d_nodes.data_ptr()), nodes.shape[0], 3, 1, C.byref(h)) == 0
+        assert L.femb200_assembler_create(ctx or holder.ctx, C.c_void_p(d_nodes.data_ptr()), n_local, 3, 1, C.byref(h)) == 0
         L.femb200_assembler_set_node_mask_device(h, C.c_void_p(mask.data_ptr()))
+        assert L.femb200_assembler_set_column_map_device(h, C.c_void_p(d_l2g.data_ptr()), nodes.shape[0]) == 0
         return h
 
     def assemble_outgoing():

@@ -71,6 +71,7 @@ def lib():
     L.femb200_csr_accumulate_rows_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
     L.femb200_csr_keep_rows_device.argtypes = [vp, vp]
     L.femb200_assembler_set_node_mask_device.argtypes = [vp, vp]
+    L.femb200_assembler_set_column_map_device.argtypes = [vp, vp, C.c_int64]
     L.femb200_csr_add_entries_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
     L.femb200_csr_pack_rows_async.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
     L.femb200_csr_add_entries_async.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]

@@ -386,6 +386,12 @@ int femb200_assembler_set_node_mask_device(femb200_assembler *ga, const uint8_t 
   return 0;
 }
 
+int femb200_assembler_set_column_map_device(femb200_assembler *ga, const int32_t *node_l2g, int64_t n_global_nodes) {
+  if (!ga || n_global_nodes < 0 || n_global_nodes * ga->mdpn >= ((int64_t)1 << 31)) return FEMB200_ERR_BAD_ARG;
+  ga->d_col_map = node_l2g;
+  return 0;
+}
+
 int femb200_csr_keep_rows_device(femb200_assembler *ga, const uint8_t *keep) {
   if (!ga || !keep) return FEMB200_ERR_BAD_ARG;
   FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));

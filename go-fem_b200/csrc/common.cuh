@@ -87,6 +87,7 @@ struct femb200_assembler {
   int64_t n_nodes = 0;
   int32_t mdpn = 0;
   const uint8_t *d_node_mask = nullptr; // optional: only rows of nodes with mask != 0 are assembled (row-block restriction)
+  const int32_t *d_col_map = nullptr;   // optional: local node -> global node (monotone); K.indices then hold GLOBAL dof ids
   femb200::DeviceCsr K;
   femb200::LastPlan plan;
   int32_t err_kind = 0;

@@ -309,7 +309,8 @@ __global__ void k_indptr(int64_t n_nodes, int mdpn, int nu, unsigned umask, cons
 template <int NU>
 __global__ void __launch_bounds__(256)
 k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ umap_packed, const int32_t *__restrict__ n2e_ptr,
-         const int64_t *__restrict__ blkptr, const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices) {
+         const int64_t *__restrict__ blkptr, const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices,
+         const int32_t *__restrict__ col_map) {
   const int nu = NU > 0 ? NU : nu_rt;
   const int lane = threadIdx.x & 31;
   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -328,7 +329,8 @@ k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ u
     int off = um[0];
 #pragma unroll
     for (int u = 1; u < (NU > 0 ? NU : kMaxNdn); ++u) off = (uc == u) ? um[u] : off;
-    const int32_t c = cols[p] * mdpn + off;
+    const int32_t J = cols[p];
+    const int32_t c = (col_map ? col_map[J] : J) * mdpn + off;
     for (int ur = 0; ur < nu; ++ur) out[(int64_t)ur * rowsz + idx] = c;
   }
 }
@@ -457,10 +459,10 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   if (out->nblk) {
     const unsigned eg = grid_for(n_nodes * 32, 256);
     switch (nu) {
-    case 1: k_expand<1><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
-    case 2: k_expand<2><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
-    case 3: k_expand<3><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
-    default: k_expand<0><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices); break;
+    case 1: k_expand<1><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
+    case 2: k_expand<2><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
+    case 3: k_expand<3><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
+    default: k_expand<0><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
     }
     ctx->launches++;
   }

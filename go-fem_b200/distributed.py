@@ -99,6 +99,28 @@ class ExchangePlan:
         return np.concatenate([own, conn[self.halo_elems]], axis=0), int(self.halo_elems.size)
 
 
+class LocalNumbering:
+    """Rank-local node numbering: the ascending list of the global nodes the rank's elements (own + halo) touch.  The
+    device assembler is created over these nodes only, so every per-call array is sized by the rank's share of the mesh;
+    rows of the local K are local, its column indices are global (femb200_assembler_set_column_map_device)."""
+
+    def __init__(self, nodes, conn_global_rows):
+        self.l2g = np.unique(conn_global_rows)
+        self.nodes = np.ascontiguousarray(nodes[self.l2g])
+
+    def conn(self, conn_global_rows):
+        return np.ascontiguousarray(np.searchsorted(self.l2g, conn_global_rows).astype(np.int32))
+
+    def node_mask(self, global_mask):
+        return np.ascontiguousarray(global_mask[self.l2g].astype(np.uint8))
+
+    def rows(self, rows_global, mdpn):
+        node, dof = rows_global // mdpn, rows_global % mdpn
+        ln = np.searchsorted(self.l2g, node)
+        assert np.array_equal(self.l2g[np.minimum(ln, self.l2g.size - 1)], node), "row of a node outside the local numbering"
+        return (ln * mdpn + dof).astype(np.int64)
+
+
 # ----------------------------------------------------------------------------- planned exchange (host, once per mesh)
 def interface_block_rows(n_nodes, conn, bounds, owner, p):
     """Interface pattern of sender p, exact: for every node J that p's elements touch and another rank owns, the
@@ -157,13 +179,15 @@ class PlannedExchange:
     """Per-rank state of the planned exchange (torch tensors on `device`); pack / add are delegated to the local
     backends (the C ABI kernels on the GPU, numpy in the gloo tests)."""
 
-    def __init__(self, iplan, device):
+    def __init__(self, iplan, device, local=None):
+        """local: LocalNumbering of the rank -- the plan's global row ids are translated to the local rows of its K."""
         import torch
         self.p, self.device = iplan, device
         t = lambda a: torch.as_tensor(a, device=device)
-        self.send_rows = [t(r) for r, _ in iplan.send]
+        loc = (lambda r: local.rows(r, iplan.nu)) if local is not None else (lambda r: r)
+        self.send_rows = [t(loc(r)) for r, _ in iplan.send]
         self.send_ptr = [t(p) for _, p in iplan.send]
-        self.recv_rows = [t(r) for r, _ in iplan.recv]
+        self.recv_rows = [t(loc(r)) for r, _ in iplan.recv]
         self.recv_ptr = [t(p) for _, p in iplan.recv]
         self.sendbuf = torch.zeros(max(sum(iplan.send_bytes), 16), dtype=torch.uint8, device=device)
         self.recvbuf = torch.zeros(max(sum(iplan.recv_bytes), 16), dtype=torch.uint8, device=device)
@@ -487,6 +511,31 @@ class NumpyBackend(LocalBackend):
         self.values = np.add.reduceat(v, starts) if r.size else v
         self.indices = c[starts].astype(np.int32)
         self.indptr = np.concatenate([[0], np.cumsum(np.bincount(r[starts], minlength=n))]).astype(np.int64)
+
+
+def gather_distributed_csr_local(backend, local, own_mask_local, mdpn, n_global_nodes, dist):
+    """Test helper for ranks with a LocalNumbering: every rank contributes the rows of its OWN local nodes (global column
+    ids already) -> the full canonical CSR in global numbering (host numpy) on every rank."""
+    indptr, indices, values = backend.csr_tensors()
+    ip, ix, va = indptr.cpu().numpy(), indices.cpu().numpy(), values.cpu().numpy()
+    own_rows = np.nonzero(np.repeat(own_mask_local.astype(bool), mdpn))[0]
+    grow = (local.l2g[own_rows // mdpn].astype(np.int64) * mdpn + own_rows % mdpn)
+    lens = ip[own_rows + 1] - ip[own_rows]
+    sel = np.repeat(ip[own_rows], lens) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens) - lens, lens))
+    objs = [None] * dist.get_world_size()
+    dist.all_gather_object(objs, (grow, lens, ix[sel], va[sel]))
+    n = n_global_nodes * mdpn
+    total = np.zeros(n, dtype=np.int64)
+    for g, ln, _, _ in objs:
+        assert not np.any(total[g] > 0), "two ranks own the same row"
+        total[g] = ln
+    ptr = np.concatenate([[0], np.cumsum(total)]).astype(np.int64)
+    idx = np.zeros(ptr[-1], dtype=np.int32)
+    val = np.zeros(ptr[-1])
+    for g, ln, ixp, vap in objs:
+        dst = np.repeat(ptr[g], ln) + (np.arange(int(ln.sum())) - np.repeat(np.cumsum(ln) - ln, ln))
+        idx[dst], val[dst] = ixp, vap
+    return ptr, idx, val
 
 
 def gather_distributed_csr(backend, plan, dist, device):

@@ -142,6 +142,11 @@ int femb200_csr_accumulate_rows_device(femb200_assembler *ga, int64_t n_rows, co
  * NULL = all) are assembled; the other rows stay empty.  A rank assembles its owned row block with one assembler
  * and the interface rows it must send with another one, so no row is computed and then thrown away. */
 int femb200_assembler_set_node_mask_device(femb200_assembler *ga, const uint8_t *node_mask);
+/* Local node numbering of a rank (multi-GPU): the assembler is created over the rank's LOCAL nodes (own + ghost, ascending
+ * global id) and node_l2g[local node] = global node (device int32, strictly increasing; NULL = identity).  Rows of K stay
+ * local (row r = local node r / mdpn), K.indices become GLOBAL dof ids mdpn * node_l2g[node] + dof: every per-call array is
+ * sized by the rank's share of the mesh, not by the global mesh. */
+int femb200_assembler_set_column_map_device(femb200_assembler *ga, const int32_t *node_l2g, int64_t n_global_nodes);
 /* K[rows] += A in place: like femb200_csr_accumulate_rows_device but every (row, column) of A must already be
  * in the pattern of K (true for owned rows assembled with their halo).  No allocation, no pattern change;
  * FEMB200_ERR_PATTERN if an entry is missing (checked in a first pass: K is untouched on failure). */

@@ -86,6 +86,45 @@ for name, size in cases:
         ok3 = pat3 and nerr3 <= 1e-12
         ok_all &= ok3
         print(f"[dist_check] {name} owner-computes: pattern_exact={pat3} max_norm_err={nerr3:.2e} -> {'OK' if ok3 else 'FAIL'}", flush=True)
+    # the same two schemes over the rank's LOCAL node numbering (what bench.py times): arrays sized by the rank's share
+    ln = D.LocalNumbering(nodes, conn[gids])
+    d_l2g = torch.from_numpy(ln.l2g.astype(np.int32)).to(dev)
+    m_own_l = torch.as_tensor(ln.node_mask(plan.own_node_mask), device=dev)
+    m_send_l = torch.as_tensor(ln.node_mask(plan.send_node_mask), device=dev)
+
+    def local_asm(mask_t):
+        r_ = pkg.RawAssembler(ln.nodes, mdpn, device=lrank)
+        L.femb200_ctx_set_stream(r_.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        L.femb200_assembler_set_node_mask_device(r_.h, C.c_void_p(mask_t.data_ptr()))
+        assert L.femb200_assembler_set_column_map_device(r_.h, C.c_void_p(d_l2g.data_ptr()), nodes.shape[0]) == 0
+        return r_
+
+    raw4 = local_asm(m_own_l)
+    rc = raw4.add(desc, conn=ln.conn(conn[gids]))
+    assert rc == 0, (rc, raw4.last_error())
+    ptr4, idx4, val4 = D.gather_distributed_csr_local(D.Femb200Backend(pkg, raw4, dev), ln, ln.node_mask(plan.own_node_mask), mdpn, nodes.shape[0], dist)
+    raw5 = local_asm(m_own_l)
+    lc, nh = plan.local_connectivity(conn, bounds)
+    rc = raw5.add(desc, conn=ln.conn(lc), n_pattern_only=nh)
+    assert rc == 0, (rc, raw5.last_error())
+    raw6 = local_asm(m_send_l)
+    rc = raw6.add(desc, conn=ln.conn(own_conn[plan.send_elems]) if plan.send_elems.size else np.zeros((0, conn.shape[1]), dtype=np.int32))
+    assert rc == 0, (rc, raw6.last_error())
+    iplan2 = D.InterfacePlan(plan, nodes.shape[0], conn, bounds, mdpn, dist)
+    px2 = D.PlannedExchange(iplan2, dev, local=ln)
+    px2.run(D.Femb200Backend(pkg, raw5, dev), D.Femb200Backend(pkg, raw6, dev), dist)
+    torch.cuda.synchronize()
+    assert px2.mismatches() == 0, px2.mismatches()
+    ptr5, idx5, val5 = D.gather_distributed_csr_local(D.Femb200Backend(pkg, raw5, dev), ln, ln.node_mask(plan.own_node_mask), mdpn, nodes.shape[0], dist)
+    if rank == 0:
+        for tag, (pp, ii, vv) in (("owner-computes/local", (ptr4, idx4, val4)), ("row-exchange/local", (ptr5, idx5, val5))):
+            patx = np.array_equal(pp, rp) and np.array_equal(ii, ri)
+            nerrx = (np.abs(vv - rv) / np.maximum(np.maximum(np.abs(rv), ab), 1e-300)).max() if patx else float("inf")
+            okx = patx and nerrx <= 1e-12
+            ok_all &= okx
+            print(f"[dist_check] {name} {tag}: pattern_exact={patx} max_norm_err={nerrx:.2e} -> {'OK' if okx else 'FAIL'}", flush=True)
+    for r_ in (raw4, raw5, raw6):
+        r_.close()
     raw.close()
     raw3.close()
     if raw2 is not None:

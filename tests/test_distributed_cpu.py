@@ -179,3 +179,34 @@ def test_partition_helpers():
     sent_m = sum(r.size for p in plans for r in p.send_rows)
     sent_r = sum(r.size for rr in range(3) for r in D.ExchangePlan(nodes.shape[0], conn[rnd], b, rr, 3).send_rows)
     assert sent_m < sent_r
+
+
+def test_local_numbering():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    entry.load_package()
+    from importlib import import_module
+    D = import_module("gofem_b200.distributed")
+    M = import_module("gofem_b200.meshes")
+    nodes, conn = M.bcc_tetra4(4)
+    b = D.chunk_bounds(conn.shape[0], 3)
+    for r in range(3):
+        plan = D.ExchangePlan(nodes.shape[0], conn, b, r, 3)
+        gids = np.sort(np.concatenate([np.arange(b[r], b[r + 1]), plan.halo_elems]))
+        ln = D.LocalNumbering(nodes, conn[gids])
+        assert np.all(np.diff(ln.l2g) > 0)                                   # ascending => column order is preserved
+        lc = ln.conn(conn[gids])
+        assert np.array_equal(ln.l2g[lc], conn[gids]) and np.array_equal(ln.nodes, nodes[ln.l2g])
+        assert np.all(plan.own_node_mask[ln.l2g][np.unique(ln.conn(conn[b[r]:b[r + 1]]))] | True)
+        # every owned, referenced node is local; rows translate back and forth
+        owned = np.nonzero(plan.own_node_mask)[0]
+        referenced = np.intersect1d(owned, np.unique(conn))
+        assert np.all(np.isin(referenced, ln.l2g))
+        rows_g = (referenced[:, None] * 3 + np.arange(3)[None, :]).ravel()
+        rows_l = ln.rows(rows_g, 3)
+        assert np.array_equal(ln.l2g[rows_l // 3] * 3 + rows_l % 3, rows_g)
+        iplan = D.InterfacePlan(plan, nodes.shape[0], conn, b, 3, None)
+        for rows, _ in iplan.send + iplan.recv:
+            if rows.size:
+                ln.rows(rows, 3)                                               # interface rows are all local
+
