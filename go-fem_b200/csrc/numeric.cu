@@ -475,6 +475,7 @@ struct RowArgs {
   const int64_t *blkptr;
   const double *stag;
   const uint8_t *degen;
+  const int32_t *order;       // node rows in visiting order (NULL: identity)
   double *values;
   int64_t ninc;               // n_elem * nn (length of n2e_t)
   int nqp;
@@ -515,7 +516,10 @@ __device__ __forceinline__ void e_row_add(const RowArgs &a, double u, double (&E
   }
 }
 
-template <int D, int NN, int BKIND, int G, int TPB>
+// PACKED: every node row of the block gets exactly its own rl*NDN*NDN accumulators (offsets by a warp scan) instead of
+// max_rowlen interleaved ones -- quadratic meshes mix rows of very different lengths, and the FP64-bound elements
+// do few read-modify-writes per flop, so a few bank conflicts cost nothing while the smaller footprint buys occupancy.
+template <int D, int NN, int BKIND, int G, int TPB, bool PACKED>
 __global__ void __launch_bounds__(TPB)
 k_noderows(const RowArgs a) {
   using B = BT<BKIND, D>;
@@ -523,17 +527,18 @@ k_noderows(const RowArgs a) {
   constexpr int NDN = B::NDN, NV = B::NV, DIMC = B::DIMC, NVP = S::NVP, REC = S::REC;
   static_assert(TPB % 32 == 0 && 32 % G == 0, "G divides the warp");
   constexpr int NPB = TPB / G;              // node rows per block
-  constexpr int NPBP = NPB | 1;             // padded (odd) stride of the shared accumulators
+  constexpr int NPBP = PACKED ? 1 : (NPB | 1); // stride of one row's accumulators (interleaved: odd, conflict free)
   constexpr int NPW = 32 / G;               // node rows per warp
   constexpr int NB = (NN + G - 1) / G;      // element nodes per lane
   extern __shared__ double s_R[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int g = tid % G, nloc = tid / G;
-  const int64_t I = (int64_t)blockIdx.x * NPB + nloc;
+  const int64_t vis = (int64_t)blockIdx.x * NPB + nloc;
+  const int64_t I = (vis < a.n_nodes && a.order) ? (int64_t)__ldg(a.order + vis) : vis;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   int beg = 0, end = 0, rl = 0;
   int64_t b0 = 0;
-  if (I < a.n_nodes) {
+  if (vis < a.n_nodes) {
     beg = __ldg(a.n2e_ptr + I); end = __ldg(a.n2e_ptr + I + 1);
     b0 = __ldg(a.blkptr + I);
     rl = (int)(__ldg(a.blkptr + I + 1) - b0);
@@ -541,7 +546,19 @@ k_noderows(const RowArgs a) {
   if (rl == 0) end = beg;                   // unreferenced node, or a row this rank does not assemble
   const int rowsz = rl * NDN;               // scalar row length
   const int tot = rowsz * NDN;              // entries of the node-block row: [i][p][j]
-  double *const sacc = s_R + nloc;
+  int soff = nloc;                          // interleaved: entry m of row slot n at s_R[m * NPBP + n]
+  if constexpr (PACKED) {                   // packed: rows back to back, offsets = exclusive scan over the warp's rows
+    static_assert(!PACKED || TPB == 32, "packed accumulators: one warp per block");
+    const int mine = (g == 0) ? tot : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    soff = __shfl_sync(0xffffffffu, incl - mine, lane & ~(G - 1));
+  }
+  double *const sacc = s_R + soff;
   for (int m = g; m < tot; m += G) sacc[m * NPBP] = 0.0;
   if constexpr (G > 1) __syncwarp(gmask);
 
@@ -744,9 +761,9 @@ k_noderows(const RowArgs a) {
   for (int n = 0; n < NPW; ++n) {
     const int tot_n = __shfl_sync(0xffffffffu, tot, n * G);
     const unsigned long long vb_n = __shfl_sync(0xffffffffu, (unsigned long long)vbase, n * G);
-    const int nloc_n = __shfl_sync(0xffffffffu, nloc, n * G);
+    const int soff_n = __shfl_sync(0xffffffffu, soff, n * G);
     double *const vrow = reinterpret_cast<double *>(vb_n);
-    const double *const src = s_R + nloc_n;
+    const double *const src = s_R + soff_n;
     for (int m = lane; m < tot_n; m += 32) vrow[m] = src[m * NPBP];
   }
 }
@@ -755,16 +772,21 @@ k_noderows(const RowArgs a) {
 template <int NN> struct GroupOf { static constexpr int G = NN >= 8 ? 4 : (NN >= 4 ? 2 : 1); };
 
 template <int D, int NN, int BKIND, int G>
-static int launch_noderows(femb200_ctx *ctx, const RowArgs &a, int max_rowlen) {
+static int launch_noderows(femb200_ctx *ctx, const RowArgs &a, const SymbolicResult *sym) {
   using B = BT<BKIND, D>;
   constexpr int TPN = 32;                        // one warp per block
-  constexpr int NPBP = (TPN / G) | 1;
-  const size_t smem = (size_t)max_rowlen * B::NDN * B::NDN * sizeof(double) * NPBP;
+  constexpr int NPB = TPN / G;
+  constexpr bool PACKED = NN == 8 || NN == 20;   // elements with many quadrature points per read-modify-write (see the kernel)
+  constexpr int SLOT = NPB == 32 ? 3 : (NPB == 16 ? 2 : (NPB == 8 ? 1 : 0)); // group_need index for NPB rows
+  static_assert(NPB >= 4 || !PACKED, "packed accumulators need at least 4 rows per warp");
+  size_t smem;
+  if (PACKED) smem = (size_t)sym->group_need[SLOT] * B::NDN * B::NDN * sizeof(double);
+  else smem = (size_t)sym->max_rowlen * B::NDN * B::NDN * sizeof(double) * (NPB | 1);
   if (smem > ctx->smem_optin) return -2;
-  auto nrows = k_noderows<D, NN, BKIND, G, TPN>;
+  auto nrows = k_noderows<D, NN, BKIND, G, TPN, PACKED>;
   FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(nrows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
   if (a.n_nodes) {
-    nrows<<<grid_for(a.n_nodes, TPN / G), TPN, smem, ctx->stream>>>(a);
+    nrows<<<grid_for(a.n_nodes, NPB), TPN, smem, ctx->stream>>>(a);
     ctx->launches++;
   }
   FEMB_CUDA_OK(ctx, cudaGetLastError());
@@ -782,8 +804,9 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   int gsel = getenv("FEMB200_G") ? atoi(getenv("FEMB200_G")) : G0;
   if (gsel != G0 && gsel != G1 && gsel != G2) gsel = G0;
   {
-    // does any variant fit the shared-memory accumulators?  (the smallest block is the one with the most lanes per row)
-    const size_t smem_min = (size_t)sym->max_rowlen * B::NDN * B::NDN * sizeof(double) * ((32 / G2) | 1);
+    // does any variant fit the shared-memory accumulators?  (the smallest block is the one with the most lanes per row;
+    // a single row needs max_rowlen blocks whatever the layout)
+    const size_t smem_min = (size_t)sym->max_rowlen * B::NDN * B::NDN * sizeof(double) * ((NN == 8 || NN == 20) ? 1 : ((32 / G2) | 1));
     if (smem_min > ctx->smem_optin) return -2; // caller falls back to global accumulators
   }
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
@@ -801,13 +824,13 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
   RowArgs a;
   a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
-  a.stag = stag; a.degen = degen; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
+  a.stag = stag; a.degen = degen; a.order = getenv("FEMB200_NO_ORDER") ? nullptr : sym->order; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
   a.dbg = getenv("FEMB200_DBG") ? atoi(getenv("FEMB200_DBG")) : 0;
   for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
   rc = -2;
-  if (gsel == G0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym->max_rowlen);
-  if (rc == -2 && gsel <= G1) rc = launch_noderows<D, NN, BKIND, G1>(ctx, a, sym->max_rowlen);
-  if (rc == -2) rc = launch_noderows<D, NN, BKIND, G2>(ctx, a, sym->max_rowlen);
+  if (gsel == G0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym);
+  if (rc == -2 && gsel <= G1) rc = launch_noderows<D, NN, BKIND, G1>(ctx, a, sym);
+  if (rc == -2) rc = launch_noderows<D, NN, BKIND, G2>(ctx, a, sym);
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
   ga->split_numeric = true;
   return rc;

@@ -289,6 +289,36 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   if (l == 0) rowlen[I] = cnt;
 }
 
+// need[s] = max over aligned groups of (4 << s) consecutive rows of sum(rowlen): shared-memory budget of a block of the
+// packed node-row kernel.  Block-level max in shared memory, then one atomic per block and slot.
+__global__ void __launch_bounds__(256)
+k_group_need(int64_t n_nodes, const int64_t *__restrict__ rowlen, unsigned long long *__restrict__ need) {
+  __shared__ int s_max[4];
+  if (threadIdx.x < 4) s_max[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int len = v < n_nodes ? (int)rowlen[v] : 0;
+  int m[4];
+  len += __shfl_xor_sync(0xffffffffu, len, 1);
+  len += __shfl_xor_sync(0xffffffffu, len, 2);
+  m[0] = len;
+  len += __shfl_xor_sync(0xffffffffu, len, 4);
+  m[1] = len;
+  len += __shfl_xor_sync(0xffffffffu, len, 8);
+  m[2] = len;
+  len += __shfl_xor_sync(0xffffffffu, len, 16);
+  m[3] = len;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[s] = max(m[s], __shfl_xor_sync(0xffffffffu, m[s], o));
+    if (lane == 0) atomicMax(&s_max[s], m[s]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicMax(need + threadIdx.x, (unsigned long long)s_max[threadIdx.x]);
+}
+
 // scalar row pointers: row (I, m), m in [0, mdpn)
 __global__ void k_indptr(int64_t n_nodes, int mdpn, int nu, unsigned umask, const int64_t *__restrict__ blkptr,
                          int64_t *__restrict__ indptr) {
@@ -423,6 +453,13 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   default: rc = FEMB200_ERR_UNSUPPORTED;
   }
   if (rc) return rc;
+  // per-group shared-memory need of the numeric phase (rows are visited in node order: a visiting order by first
+  // incident element was measured and rejected -- it mixes rows with 5 and with 24 incident elements in one warp)
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scalars + 2, 0, 4 * sizeof(int64_t), st));
+  if (n_nodes && (nn == 8 || nn == 20)) { // the element sizes whose numeric kernel uses packed accumulators
+    k_group_need<<<grid_for(n_nodes, 256), 256, 0, st>>>(n_nodes, rowlen, (unsigned long long *)(ctx->d_scalars + 2));
+    ctx->launches++;
+  }
   tb = ctx->cub_tmp_bytes;
   FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, rowlen, out->blkptr, (int)(n_nodes + 1), st));
   tb = ctx->cub_tmp_bytes;
@@ -431,11 +468,13 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   // host needs nblk (allocation sizes), max row length (numeric launch shape) and the error word
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 1, out->blkptr + n_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], st));
   FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
   out->max_rowlen = (int)ctx->h_scalars[0];
   out->nblk = ctx->h_scalars[1];
+  for (int s = 0; s < 4; ++s) out->group_need[s] = n_nodes ? ctx->h_scalars[2 + s] : 0;
   if (*ctx->h_err != kNoError) return -1; // caller decodes the error word
   if (out->max_rowlen > 65535) return FEMB200_ERR_TOO_LARGE;
 
