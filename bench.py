@@ -179,7 +179,17 @@ def run_reference(args):
     if rank != 0:
         return
     name = args.config
-    size = args.size or {"tetra4": 32, "quad4": 700, "hexa8": 40, "tetra10": 16, "hexa20": 12}[name]
+    if args.size:
+        size = args.size
+    elif name == "tetra4":
+        # bounded sample: about 90 s of CPU work for the whole run at ~1.1e5 elements/s (single thread), never more than the
+        # workload itself; BCC cube N -> 12 N^2 (N-1) elements
+        budget = 90.0 / max(1, args.steps + args.warmup) * 1.1e5
+        size = 8
+        while size < 48 and 12 * (size + 1) ** 2 * size <= budget:
+            size += 1
+    else:
+        size = {"quad4": 700, "hexa8": 40, "tetra10": 16, "hexa20": 12}[name]
     w = make_workload(name, size)
     full = make_workload_desc(name, args.size)
     times = []

@@ -32,12 +32,15 @@ def launches(src, dst, cmd=""):
     for d in data:
         n = re.sub(r"\(.*", "", re.sub(r"<.*", "", d["Kernel Name"]))[:70]
         agg.setdefault(n, []).append(float(d["Metric Value"].replace(",", "")) / 1e3)
-    tot = sum(sum(v) for v in agg.values())
+    other = lambda n: ("k_probe" in n) or ("at::" in n)   # roofline probes and torch's L2-flush fill: not part of a step
+    tot = sum(sum(v) for n, v in agg.items() if not other(n))
     with open(dst, "w") as f:
         f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n`{cmd}`\n\n")
-        f.write("| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|\n")
+        f.write("Share = share of the assembly kernels of one step (roofline probe kernels and torch's L2-flush fill are listed but excluded).\n\n")
+        f.write("| kernel | launches | mean us | total us | share of step kernels |\n|---|---|---|---|---|\n")
         for n, v in agg.items():
-            f.write(f"| {n} | {len(v)} | {sum(v)/len(v):.1f} | {sum(v):.1f} | {100*sum(v)/tot:.1f}% |\n")
+            sh = "-" if other(n) else f"{100*sum(v)/tot:.1f}%"
+            f.write(f"| {n} | {len(v)} | {sum(v)/len(v):.1f} | {sum(v):.1f} | {sh} |\n")
     print(open(dst).read())
 
 
