@@ -60,6 +60,7 @@ def lib():
     L.femb200_assembler_destroy.argtypes = [vp]
     L.femb200_add_isoparametric.argtypes = [vp, C.POINTER(ElemDesc), vp, C.c_int32, C.c_int32, C.c_int64]
     L.femb200_last_error.argtypes = [vp, _i32p, _i64p, _i32p]
+    L.femb200_reassemble.argtypes = [vp, C.POINTER(ElemDesc), vp, C.c_int32]
     L.femb200_total_dofs.argtypes = [vp]
     L.femb200_total_dofs.restype = C.c_int64
     L.femb200_nnz.argtypes = [vp]
@@ -474,6 +475,15 @@ class RawAssembler:
         k, e, q = C.c_int32(), C.c_int64(), C.c_int32()
         lib().femb200_last_error(self.h, C.byref(k), C.byref(e), C.byref(q))
         return k.value, e.value, q.value
+
+    def reassemble(self, desc, nodes=None, nodes_device_ptr=None):
+        """Numeric-only re-assembly on the cached pattern (femb200_reassemble)."""
+        if nodes_device_ptr is not None:
+            return lib().femb200_reassemble(self.h, C.byref(desc), C.c_void_p(nodes_device_ptr), 1)
+        if nodes is not None:
+            nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+            return lib().femb200_reassemble(self.h, C.byref(desc), C.c_void_p(nodes.ctypes.data), 0)
+        return lib().femb200_reassemble(self.h, C.byref(desc), None, 0)
 
     def nnz(self):
         return lib().femb200_nnz(self.h)

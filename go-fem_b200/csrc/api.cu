@@ -116,6 +116,7 @@ static void free_plan(femb200_assembler *ga) {
   dev_free(ctx, ga->plan.n2e_t);
   dev_free(ctx, ga->plan.pos16);
   dev_free(ctx, ga->plan.blkptr);
+  dev_free(ctx, ga->plan.conn32);
   ga->plan = LastPlan();
 }
 
@@ -181,7 +182,7 @@ static int stage_conn(femb200_assembler *ga, const void *conn, bool is64, bool o
   femb200_ctx *ctx = ga->ctx;
   *staged = nullptr;
   int rc;
-  if ((rc = scratch_alloc(ctx, conn32, (size_t)n))) return rc;
+  if ((rc = dev_alloc(ctx, conn32, (size_t)n))) return rc; // pool, not scratch: the plan keeps it (femb200_reassemble)
   const void *d_in = conn;
   if (!on_device && n) {
     size_t bytes = (size_t)n * (is64 ? 8 : 4);
@@ -221,8 +222,8 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   void *staged = nullptr;
   double *d_tab = nullptr;
   SymbolicResult sym;
-  ScratchScope scratch_scope(ctx); // conn32, staged, d_tab, symbolic / numeric temporaries: released on every return path
-  auto cleanup = [&]() {};
+  ScratchScope scratch_scope(ctx); // staged, d_tab, symbolic / numeric temporaries: released on every return path
+  auto cleanup = [&]() { dev_free(ctx, conn32); };
   auto drop_sym = [&]() {
     dev_free(ctx, sym.n2e_ptr); dev_free(ctx, sym.n2e_t); dev_free(ctx, sym.pos16); dev_free(ctx, sym.blkptr);
     dev_free(ctx, sym.csr.indptr); dev_free(ctx, sym.csr.indices); dev_free(ctx, sym.csr.values);
@@ -254,6 +255,11 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   free_plan(ga);
   ga->plan.nn = sh.nn; ga->plan.nu = sh.nu; ga->plan.n_elem = n_elem;
   ga->plan.n2e_ptr = sym.n2e_ptr; ga->plan.n2e_t = sym.n2e_t; ga->plan.pos16 = sym.pos16; ga->plan.blkptr = sym.blkptr;
+  ga->plan.conn32 = conn32; conn32 = nullptr;
+  ga->plan.n_numeric = n_elem - n_pattern_only;
+  ga->plan.d = sh.d; ga->plan.ndn = sh.ndn; ga->plan.bkind = sh.bkind; ga->plan.max_rowlen = sym.max_rowlen; ga->plan.identity = sh.identity;
+  for (int s = 0; s < 4; ++s) ga->plan.group_need[s] = sym.group_need[s];
+  ga->plan.matches_K = (ga->K.nnz == 0);
   rc = csr_merge_into(ga, &sym.csr);
   cleanup();
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[6], st));
@@ -264,6 +270,81 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   for (int i = 0; i < 6; ++i)
     if (cudaEventElapsedTime(&ms, ctx->ev[pairs[i][0]], ctx->ev[pairs[i][1]]) == cudaSuccess) ga->phase_ms[i] = ms;
   if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]) == cudaSuccess) ga->phase_ms[6] = ms;
+  ga->phase_ms[7] = (float)(ctx->launches - launches0);
+  if (ga->split_numeric) {
+    if (cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]) == cudaSuccess) ga->phase_ms[8] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ga->phase_ms[9] = ms;
+  }
+  return 0;
+}
+
+int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, const double *nodes, int32_t nodes_on_device) {
+  if (!ga) return FEMB200_ERR_BAD_ARG;
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  LastPlan &pl = ga->plan;
+  if (!pl.conn32 || !pl.matches_K || ga->K.nnz == 0) return FEMB200_ERR_BAD_ARG; // exactly one committed call on this assembler
+  ga->err_kind = 0; ga->err_elem = -1; ga->err_qp = -1;
+  ElemShape sh;
+  std::vector<double> blob;
+  int rc = prepare(ga, desc, &sh, &blob);
+  if (!rc && (sh.nn != pl.nn || sh.ndn != pl.ndn || sh.d != pl.d || sh.nu != pl.nu || sh.identity != pl.identity)) rc = FEMB200_ERR_BAD_ARG;
+  if (rc) { ga->err_kind = rc; return rc; }
+  for (float &f : ga->phase_ms) f = 0.f;
+  ga->split_numeric = false;
+  const int64_t launches0 = ctx->launches;
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
+  // new coordinates (same node count): nonlinear / moving-mesh re-assembly.  They replace the old ones only if the call
+  // succeeds, so a failed re-assembly leaves the assembler exactly as it was.
+  const double *old_nodes = ga->d_nodes;
+  const bool old_own = ga->own_nodes;
+  double *fresh_nodes = nullptr;
+  if (nodes) {
+    if (nodes_on_device) {
+      ga->d_nodes = nodes;
+      ga->own_nodes = false;
+    } else {
+      if ((rc = dev_alloc(ctx, &fresh_nodes, (size_t)ga->n_nodes * 3))) return rc;
+      FEMB_CUDA_OK(ctx, cudaMemcpyAsync(fresh_nodes, nodes, sizeof(double) * 3 * ga->n_nodes, cudaMemcpyHostToDevice, st));
+      ga->d_nodes = fresh_nodes;
+      ga->own_nodes = true;
+    }
+  }
+  auto restore_nodes = [&]() {
+    dev_free(ctx, fresh_nodes);
+    ga->d_nodes = old_nodes;
+    ga->own_nodes = old_own;
+  };
+  *ctx->h_err = kNoError;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+  ScratchScope scratch_scope(ctx);
+  double *d_tab = nullptr, *newvals = nullptr;
+  if ((rc = scratch_alloc(ctx, &d_tab, blob.size()))) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st));
+  if ((rc = dev_alloc(ctx, &newvals, (size_t)ga->K.nnz))) return rc;
+  SymbolicResult sym;
+  sym.n2e_ptr = pl.n2e_ptr; sym.n2e_t = pl.n2e_t; sym.pos16 = pl.pos16; sym.blkptr = pl.blkptr;
+  sym.max_rowlen = pl.max_rowlen;
+  for (int s = 0; s < 4; ++s) sym.group_need[s] = pl.group_need[s];
+  sym.csr.n_rows = ga->K.n_rows; sym.csr.nnz = ga->K.nnz; sym.csr.indptr = ga->K.indptr; sym.csr.indices = ga->K.indices;
+  sym.csr.values = newvals;
+  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
+  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), pl.conn32, pl.n_numeric, &sym);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
+  }
+  if (!rc) rc = decode_error(ga);
+  if (rc) { dev_free(ctx, newvals); restore_nodes(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; } // K untouched
+  if (nodes && old_own) { double *d = const_cast<double *>(old_nodes); dev_free(ctx, d); }
+  dev_free(ctx, ga->K.values);
+  ga->K.values = newvals;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ga->phase_ms[4] = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]) == cudaSuccess) ga->phase_ms[6] = ms;
   ga->phase_ms[7] = (float)(ctx->launches - launches0);
   if (ga->split_numeric) {
     if (cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]) == cudaSuccess) ga->phase_ms[8] = ms;
@@ -458,7 +539,7 @@ int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
   }
   if (!rc) rc = decode_error(ga);
-  dev_free(ctx, d_tab); dev_free(ctx, d_u); dev_free(ctx, d_s); dev_free(ctx, d_dofmap);
+  dev_free(ctx, conn32); dev_free(ctx, d_tab); dev_free(ctx, d_u); dev_free(ctx, d_s); dev_free(ctx, d_dofmap);
   cudaStreamSynchronize(st);
   if (rc) ga->err_kind = rc;
   return rc;

@@ -52,6 +52,13 @@ struct LastPlan {
   uint32_t *n2e_t = nullptr;    // [n_elem*nn] t = e*nn + a, grouped by node, ascending
   uint16_t *pos16 = nullptr;    // [n_elem*nn][nn] row-local block position
   int64_t *blkptr = nullptr;    // [n_nodes+1] node-block row offsets (of THIS call's pattern)
+  // kept for femb200_reassemble (numeric-only re-assembly on the cached pattern)
+  int32_t *conn32 = nullptr;    // [n_elem*nn] validated connectivity
+  int64_t n_numeric = 0;        // elements [n_numeric, n_elem) are pattern-only
+  int d = 0, ndn = 0, bkind = 0, max_rowlen = 0;
+  int64_t group_need[4] = {0, 0, 0, 0};
+  bool identity = false;
+  bool matches_K = false;       // K's pattern is exactly this call's pattern (no other call has been merged in)
 };
 
 } // namespace femb200

@@ -115,6 +115,36 @@ func (a *Assembler) AddIsoparametric(d *Desc, conn []int, nElem int) error {
 	return fmt.Errorf("femb200: status %d: %s", int(rc), C.GoString(C.femb200_last_cuda_error(a.ctx)))
 }
 
+// Reassemble recomputes the values of K on the cached pattern of the single AddIsoparametric call this assembler has
+// committed (femb200_reassemble): new material / quadrature tables in d, optional new node coordinates (nil = keep).
+// Additive API: the reference rebuilds pattern and values on every call.
+func (a *Assembler) Reassemble(d *Desc, nodesXYZ unsafe.Pointer) error {
+	var cd C.femb200_elem_desc
+	cd.d, cd.nn, cd.ndn, cd.nqp, cd.dimC = C.int32_t(d.D), C.int32_t(d.NN), C.int32_t(d.NDN), C.int32_t(d.NQP), C.int32_t(d.DimC)
+	cd.bkind = C.int32_t(d.Kind)
+	cd.model_dofs_per_node = C.int32_t(d.ModelDofsPerNode)
+	npg, dnpg, wpg, cm := cDoubles(d.Npg), cDoubles(d.DNpg), cDoubles(d.Wpg), cDoubles(d.C)
+	dm := (*C.int32_t)(C.malloc(C.size_t(4 * len(d.DofMap))))
+	defer C.free(unsafe.Pointer(npg))
+	defer C.free(unsafe.Pointer(dnpg))
+	defer C.free(unsafe.Pointer(wpg))
+	defer C.free(unsafe.Pointer(cm))
+	defer C.free(unsafe.Pointer(dm))
+	copy(unsafe.Slice((*int32)(unsafe.Pointer(dm)), len(d.DofMap)), d.DofMap)
+	cd.Npg, cd.dNpg, cd.wpg, cd.C, cd.dofmap = npg, dnpg, wpg, cm, dm
+	rc := C.femb200_reassemble(a.ga, &cd, (*C.double)(nodesXYZ), 0 /* host */)
+	if rc == 0 {
+		return nil
+	}
+	var kind, qp C.int32_t
+	var elem C.int64_t
+	C.femb200_last_error(a.ga, &kind, &elem, &qp)
+	if rc >= 1 && rc <= 8 {
+		return &ElemError{Kind: int(rc), QP: int(qp), Elem: int64(elem)}
+	}
+	return fmt.Errorf("femb200: status %d: %s", int(rc), C.GoString(C.femb200_last_cuda_error(a.ctx)))
+}
+
 func cDoubles(v []float64) *C.double {
 	p := (*C.double)(C.malloc(C.size_t(8 * len(v))))
 	copy(unsafe.Slice((*float64)(unsafe.Pointer(p)), len(v)), v)

@@ -431,6 +431,47 @@ def test_strains_match_oracle(pkg, O, meshes, name, size, mode, flags):
     assert np.allclose(s, ref, rtol=1e-11, atol=1e-13 * np.abs(ref).max())
 
 
+# ---- numeric-only re-assembly on the cached pattern (femb200_reassemble) -----------------------------
+@pytest.mark.parametrize("name,size,mode", [("hexa8", 5, 0), ("tetra4", 6, 0), ("quad4", 12, 1), ("tetra10", 3, 0)])
+def test_reassemble_numeric_only(pkg, O, meshes, name, size, mode):
+    nodes, conn = meshes.mesh_for(name, size)
+    flags = KINDS[name]["flags"]
+    mdpn = bin(flags).count("1")
+    ra = pkg.RawAssembler(nodes, mdpn)
+    d1 = ra.make_desc(elem_of(pkg, name), constituter_of(pkg, mode, 200e9, 0.3))
+    assert ra.add(d1, conn=conn) == 0
+    ip, ix, v1 = ra.csr()
+    # doubled Young modulus: every C entry doubles exactly => K doubles bitwise; pattern untouched
+    d2 = ra.make_desc(elem_of(pkg, name), constituter_of(pkg, mode, 400e9, 0.3))
+    assert ra.reassemble(d2) == 0
+    ip2, ix2, v2 = ra.csr()
+    assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2) and np.array_equal(v2, 2.0 * v1)
+    assert ra.phase_ms()["adjacency"] == 0.0 and ra.phase_ms()["k_rows"] > 0.0      # no symbolic phase ran
+    # moved nodes: bitwise equal to a fresh assembly on the moved mesh
+    rng = np.random.default_rng(3)
+    nodes2 = nodes + 1e-3 * rng.standard_normal(nodes.shape) * (np.abs(nodes).max() / size)
+    if nodes.shape[1] == 3 and name in ("quad4",):
+        nodes2[:, 2] = nodes[:, 2]
+    assert ra.reassemble(d1, nodes=nodes2) == 0
+    _, _, v3 = ra.csr()
+    fresh = pkg.RawAssembler(nodes2, mdpn)
+    assert fresh.add(fresh.make_desc(elem_of(pkg, name), constituter_of(pkg, mode, 200e9, 0.3)), conn=conn) == 0
+    fp, fi, fv = fresh.csr()
+    assert np.array_equal(fp, ip) and np.array_equal(fi, ix) and np.array_equal(fv, v3)
+    # an element error leaves K untouched (assembler_isoparametric.go:118-120)
+    bad = nodes2.copy()
+    e0 = conn[conn.shape[0] // 2]
+    bad[e0[0]], bad[e0[1]] = nodes2[e0[1]].copy(), nodes2[e0[0]].copy()          # swap two nodes: inverted element(s)
+    rc = ra.reassemble(d1, nodes=bad)
+    assert rc in (pkg.ERR_NEG_DET, pkg.ERR_ZERO_DET) if hasattr(pkg, "ERR_NEG_DET") else rc in (1, 2)
+    _, _, v4 = ra.csr()
+    assert np.array_equal(v4, v3)
+    # a second AddIsoparametric on the same assembler invalidates the cached plan for re-assembly
+    assert ra.add(d1, conn=conn) == 0
+    assert ra.reassemble(d1) == 20
+    ra.close(); fresh.close()
+
+
 # ---- BASELINE config 1 at full size: size-independent properties ----------------------------------------
 def test_config1_full_size_properties(pkg, O, meshes):
     """Tetra4 BCC N=48: 1,299,456 elements / 684,723 dofs (benchmark_test.go largest case).  The oracle is
