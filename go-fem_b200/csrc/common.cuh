@@ -177,8 +177,7 @@ struct SymbolicResult {
   int64_t *blkptr = nullptr;
   int64_t nblk = 0;
   int max_rowlen = 0;
-  int32_t *order = nullptr;   // scratch: node rows in visiting order (first incident element ascending; inactive rows last)
-  int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive visited rows of sum(rowlen)
+  int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive rows of sum(rowlen)
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)
 };
 

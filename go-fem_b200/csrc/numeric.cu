@@ -475,11 +475,9 @@ struct RowArgs {
   const int64_t *blkptr;
   const double *stag;
   const uint8_t *degen;
-  const int32_t *order;       // node rows in visiting order (NULL: identity)
   double *values;
   int64_t ninc;               // n_elem * nn (length of n2e_t)
   int nqp;
-  int dbg;                    // FEMB200_DBG experiment bits (0 in production)
   double C[kMaxDimC * kMaxDimC]; // constitutive matrix (row-major dimC x dimC): kernel-parameter space = constant bank
 };
 
@@ -533,12 +531,11 @@ k_noderows(const RowArgs a) {
   extern __shared__ double s_R[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int g = tid % G, nloc = tid / G;
-  const int64_t vis = (int64_t)blockIdx.x * NPB + nloc;
-  const int64_t I = (vis < a.n_nodes && a.order) ? (int64_t)__ldg(a.order + vis) : vis;
+  const int64_t I = (int64_t)blockIdx.x * NPB + nloc;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   int beg = 0, end = 0, rl = 0;
   int64_t b0 = 0;
-  if (vis < a.n_nodes) {
+  if (I < a.n_nodes) {
     beg = __ldg(a.n2e_ptr + I); end = __ldg(a.n2e_ptr + I + 1);
     b0 = __ldg(a.blkptr + I);
     rl = (int)(__ldg(a.blkptr + I + 1) - b0);
@@ -696,9 +693,7 @@ k_noderows(const RowArgs a) {
     if (!last_q) { ++q; return; }
     // 3. end of the element: ordered accumulation into the shared row accumulators.  The nn column blocks of
     // one element are distinct unless the element is collapsed (a repeated node, flagged by k_geometry).
-    if (a.dbg & 2) {
-      if (acc[0][0][0] == 1.2345) sacc[0] = 1.0;
-    } else if (!dg) {
+    if (!dg) {
 #pragma unroll
       for (int i = 0; i < NDN; ++i) {
         double old[NB][NDN];
@@ -756,7 +751,6 @@ k_noderows(const RowArgs a) {
   // with every row => 256-byte coalesced stores
   __syncwarp();
   double *const vbase = a.values + (int64_t)NDN * NDN * b0;
-  if (a.dbg & 1) { if (sacc[0] == 1.2345) vbase[0] = 1.0; return; }
 #pragma unroll 1
   for (int n = 0; n < NPW; ++n) {
     const int tot_n = __shfl_sync(0xffffffffu, tot, n * G);
@@ -824,8 +818,7 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
   RowArgs a;
   a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
-  a.stag = stag; a.degen = degen; a.order = getenv("FEMB200_NO_ORDER") ? nullptr : sym->order; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
-  a.dbg = getenv("FEMB200_DBG") ? atoi(getenv("FEMB200_DBG")) : 0;
+  a.stag = stag; a.degen = degen; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
   for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
   rc = -2;
   if (gsel == G0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym);

@@ -18,4 +18,4 @@ for it in range(6):
     L.femb200_assembler_destroy(h)
     if it >= 2: res.append([float(x) for x in ph])
 m = np.mean(res, axis=0)
-print(os.environ.get("FEMB200_DBG", "0"), w["desc"][:40], "rc", rc, " ".join(f"{n}={v:.3f}" for n, v in zip(pkg.TIMER_NAMES, m)))
+print(os.environ.get("FEMB200_G", "-"), w["desc"][:40], "rc", rc, " ".join(f"{n}={v:.3f}" for n, v in zip(pkg.TIMER_NAMES, m)))
