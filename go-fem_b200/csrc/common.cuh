@@ -54,6 +54,8 @@ struct LastPlan {
   int64_t *blkptr = nullptr;    // [n_nodes+1] node-block row offsets (of THIS call's pattern)
   // kept for femb200_reassemble (numeric-only re-assembly on the cached pattern)
   int32_t *conn32 = nullptr;    // [n_elem*nn] validated connectivity
+  int32_t *order = nullptr;     // two-class visiting order (see SymbolicResult), or NULL
+  int64_t n_short = 0;
   int64_t n_numeric = 0;        // elements [n_numeric, n_elem) are pattern-only
   int d = 0, ndn = 0, bkind = 0, max_rowlen = 0;
   int64_t group_need[4] = {0, 0, 0, 0};
@@ -177,6 +179,8 @@ struct SymbolicResult {
   int64_t *blkptr = nullptr;
   int64_t nblk = 0;
   int max_rowlen = 0;
+  int32_t *order = nullptr;   // two-class visiting order of the node rows (short rows first), or NULL
+  int64_t n_short = 0;        // rows [0, n_short) of `order` have rowlen <= max_rowlen / 2
   int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive rows of sum(rowlen)
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)
 };

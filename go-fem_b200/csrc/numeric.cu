@@ -475,6 +475,8 @@ struct RowArgs {
   const int64_t *blkptr;
   const double *stag;
   const uint8_t *degen;
+  const int32_t *order;       // visiting order of the node rows (NULL: identity)
+  int64_t v0, v1;             // visiting range of this launch
   double *values;
   int64_t ninc;               // n_elem * nn (length of n2e_t)
   int nqp;
@@ -531,7 +533,8 @@ k_noderows(const RowArgs a) {
   extern __shared__ double s_R[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int g = tid % G, nloc = tid / G;
-  const int64_t I = (int64_t)blockIdx.x * NPB + nloc;
+  const int64_t vis = a.v0 + (int64_t)blockIdx.x * NPB + nloc;
+  const int64_t I = vis < a.v1 ? (a.order ? (int64_t)__ldg(a.order + vis) : vis) : a.n_nodes;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   int beg = 0, end = 0, rl = 0;
   int64_t b0 = 0;
@@ -765,22 +768,25 @@ k_noderows(const RowArgs a) {
 // lanes per node row: default per element size, FEMB200_G overrides (tuning); larger G = less shared memory per block
 template <int NN> struct GroupOf { static constexpr int G = NN >= 8 ? 4 : (NN >= 4 ? 2 : 1); };
 
+// one launch of the node-row kernel over the visiting range [v0, v1) with accumulators for rows of <= rowlen_cap blocks
 template <int D, int NN, int BKIND, int G>
-static int launch_noderows(femb200_ctx *ctx, const RowArgs &a, const SymbolicResult *sym) {
+static int launch_noderows(femb200_ctx *ctx, const RowArgs &a0, const SymbolicResult *sym, const int32_t *order, int64_t v0, int64_t v1,
+                           int64_t rowlen_cap) {
   using B = BT<BKIND, D>;
   constexpr int TPN = 32;                        // one warp per block
   constexpr int NPB = TPN / G;
   constexpr bool PACKED = NN == 8 || NN == 20;   // elements with many quadrature points per read-modify-write (see the kernel)
   constexpr int SLOT = NPB == 32 ? 3 : (NPB == 16 ? 2 : (NPB == 8 ? 1 : 0)); // group_need index for NPB rows
   static_assert(NPB >= 4 || !PACKED, "packed accumulators need at least 4 rows per warp");
-  size_t smem;
-  if (PACKED) smem = (size_t)sym->group_need[SLOT] * B::NDN * B::NDN * sizeof(double);
-  else smem = (size_t)sym->max_rowlen * B::NDN * B::NDN * sizeof(double) * (NPB | 1);
+  const size_t smem = PACKED ? (size_t)sym->group_need[SLOT] * B::NDN * B::NDN * sizeof(double)
+                             : (size_t)rowlen_cap * B::NDN * B::NDN * sizeof(double) * (NPB | 1);
   if (smem > ctx->smem_optin) return -2;
   auto nrows = k_noderows<D, NN, BKIND, G, TPN, PACKED>;
   FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(nrows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-  if (a.n_nodes) {
-    nrows<<<grid_for(a.n_nodes, NPB), TPN, smem, ctx->stream>>>(a);
+  RowArgs a = a0;
+  a.order = order; a.v0 = v0; a.v1 = v1;
+  if (v1 > v0) {
+    nrows<<<grid_for(v1 - v0, NPB), TPN, smem, ctx->stream>>>(a);
     ctx->launches++;
   }
   FEMB_CUDA_OK(ctx, cudaGetLastError());
@@ -818,12 +824,20 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
   RowArgs a;
   a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
-  a.stag = stag; a.degen = degen; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
+  a.stag = stag; a.degen = degen; a.order = nullptr; a.v0 = 0; a.v1 = ga->n_nodes; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
   for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
   rc = -2;
-  if (gsel == G0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym);
-  if (rc == -2 && gsel <= G1) rc = launch_noderows<D, NN, BKIND, G1>(ctx, a, sym);
-  if (rc == -2) rc = launch_noderows<D, NN, BKIND, G2>(ctx, a, sym);
+  const int64_t nn_ = a.n_nodes;
+  constexpr bool PACKED = NN == 8 || NN == 20;
+  if (!PACKED && sym->order && sym->n_short > 0 && sym->n_short < nn_ && gsel == G0) {
+    // two launches (see k_class_flags): short rows (rowlen <= max/2) with half the accumulators per row, then the long
+    // (and empty) rows.  (More lanes per row for the long class was measured: no difference.)
+    rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym, sym->order, 0, sym->n_short, sym->max_rowlen / 2);
+    if (rc == 0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym, sym->order, sym->n_short, nn_, sym->max_rowlen);
+  }
+  if (rc == -2 && gsel == G0) rc = launch_noderows<D, NN, BKIND, G0>(ctx, a, sym, nullptr, 0, nn_, sym->max_rowlen);
+  if (rc == -2 && gsel <= G1) rc = launch_noderows<D, NN, BKIND, G1>(ctx, a, sym, nullptr, 0, nn_, sym->max_rowlen);
+  if (rc == -2) rc = launch_noderows<D, NN, BKIND, G2>(ctx, a, sym, nullptr, 0, nn_, sym->max_rowlen);
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
   ga->split_numeric = true;
   return rc;

@@ -14,6 +14,7 @@
 //   scan(rowlen) -> blkptr;  expand -> indptr (int64), indices (int32)
 #include "common.cuh"
 #include <cub/cub.cuh>
+#include <cstring>
 
 namespace femb200 {
 
@@ -319,6 +320,17 @@ k_group_need(int64_t n_nodes, const int64_t *__restrict__ rowlen, unsigned long 
   if (threadIdx.x < 4) atomicMax(need + threadIdx.x, (unsigned long long)s_max[threadIdx.x]);
 }
 
+// Two-class visiting order for meshes whose rows differ a lot in length (quadratic tetrahedra: vertex rows are 2-3x
+// longer than mid-edge rows): rows with 0 < rowlen <= max/2 are "short".  The numeric kernel is launched once per class
+// with the shared memory that class needs, which doubles the resident warps of the short class.
+__global__ void k_class_flags(int64_t n_nodes, const int64_t *__restrict__ rowlen, const int64_t *__restrict__ d_max,
+                              uint8_t *__restrict__ flag) {
+  const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= n_nodes) return;
+  const int64_t rl = rowlen[I];
+  flag[I] = (rl > 0 && 2 * rl <= *d_max) ? 1 : 0;
+}
+
 // scalar row pointers: row (I, m), m in [0, mdpn)
 __global__ void k_indptr(int64_t n_nodes, int mdpn, int nu, unsigned umask, const int64_t *__restrict__ blkptr,
                          int64_t *__restrict__ indptr) {
@@ -465,16 +477,30 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   tb = ctx->cub_tmp_bytes;
   FEMB_CUDA_OK(ctx, cub::DeviceReduce::Max(ctx->cub_tmp, tb, rowlen, ctx->d_scalars, (int)(n_nodes + 1), st));
   ctx->launches += 4;
+  if (nn == 10 && n_nodes && !getenv("FEMB200_ONE_CLASS")) { // two-class visiting order (see k_class_flags)
+    uint8_t *flag = nullptr;
+    if ((rc = scratch_alloc(ctx, &flag, n_nodes))) return rc;
+    if ((rc = dev_alloc(ctx, &out->order, n_nodes))) return rc;
+    k_class_flags<<<grid_for(n_nodes, 256), 256, 0, st>>>(n_nodes, rowlen, ctx->d_scalars, flag);
+    size_t tmp6 = 0;
+    cub::CountingInputIterator<int32_t> ids(0);
+    cub::DevicePartition::Flagged(nullptr, tmp6, ids, flag, out->order, ctx->d_scalars + 6, (int)n_nodes, st);
+    if ((rc = ensure_cub_tmp(ctx, tmp6 + 256))) return rc;
+    tb = ctx->cub_tmp_bytes;
+    FEMB_CUDA_OK(ctx, cub::DevicePartition::Flagged(ctx->cub_tmp, tb, ids, flag, out->order, ctx->d_scalars + 6, (int)n_nodes, st));
+    ctx->launches += 3;
+  }
   // host needs nblk (allocation sizes), max row length (numeric launch shape) and the error word
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 1, out->blkptr + n_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], st));
   FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
   out->max_rowlen = (int)ctx->h_scalars[0];
   out->nblk = ctx->h_scalars[1];
   for (int s = 0; s < 4; ++s) out->group_need[s] = n_nodes ? ctx->h_scalars[2 + s] : 0;
+  if (out->order) out->n_short = ctx->h_scalars[6];
   if (*ctx->h_err != kNoError) return -1; // caller decodes the error word
   if (out->max_rowlen > 65535) return FEMB200_ERR_TOO_LARGE;
 

@@ -472,6 +472,96 @@ def test_reassemble_numeric_only(pkg, O, meshes, name, size, mode):
     ra.close(); fresh.close()
 
 
+# ---- multi-GPU building blocks exercised on one GPU -------------------------------------------------------------------
+def _dev(t):
+    import ctypes as C
+    return C.c_void_p(t.data_ptr())
+
+
+def test_pack_rows_and_add_entries_async(pkg, meshes):
+    """femb200_csr_pack_rows_async / femb200_csr_add_entries_async (the planned interface exchange): packing rows of K and
+    adding them back doubles exactly those rows; a plan that contradicts K is counted in the mismatch word."""
+    import torch
+    nodes, conn = meshes.mesh_for("tetra4", 5)
+    ra = pkg.RawAssembler(nodes, 3)
+    desc = ra.make_desc(pkg.elements.Tetra4(), pkg.solids.Isotropic(200e9, 0.3).Solid3D())
+    assert ra.add(desc, conn=conn) == 0
+    ip, ix, v0 = ra.csr()
+    dev = torch.device("cuda", 0)
+    rows = np.array([3, 4, 5, 60, 61, 62, 200], dtype=np.int64)
+    lens = ip[rows + 1] - ip[rows]
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    t_rows, t_ptr = torch.from_numpy(rows).to(dev), torch.from_numpy(ptr).to(dev)
+    oi = torch.zeros(int(ptr[-1]), dtype=torch.int32, device=dev)
+    ov = torch.zeros(int(ptr[-1]), dtype=torch.float64, device=dev)
+    mism = torch.zeros(1, dtype=torch.int64, device=dev)
+    L = pkg.lib()
+    assert L.femb200_csr_pack_rows_async(ra.h, rows.size, _dev(t_rows), _dev(t_ptr), _dev(oi), _dev(ov), _dev(mism)) == 0
+    assert L.femb200_sync(ra.ctx) == 0
+    for w, r in enumerate(rows):
+        assert np.array_equal(oi[ptr[w]:ptr[w + 1]].cpu().numpy(), ix[ip[r]:ip[r + 1]])
+        assert np.array_equal(ov[ptr[w]:ptr[w + 1]].cpu().numpy(), v0[ip[r]:ip[r + 1]])
+    assert L.femb200_csr_add_entries_async(ra.h, rows.size, _dev(t_rows), _dev(t_ptr), _dev(oi), _dev(ov), _dev(mism)) == 0
+    assert L.femb200_sync(ra.ctx) == 0
+    _, _, v1 = ra.csr()
+    expect = v0.copy()
+    for r in rows:
+        expect[ip[r]:ip[r + 1]] *= 2.0
+    assert np.array_equal(v1, expect) and int(mism.item()) == 0
+    # a plan with a wrong row length, and an entry outside the pattern, are both counted
+    bad_ptr = ptr + np.arange(ptr.size, dtype=np.int64)            # every row one entry longer than K holds
+    t_bad = torch.from_numpy(bad_ptr).to(dev)
+    oi2 = torch.zeros(int(bad_ptr[-1]), dtype=torch.int32, device=dev)
+    ov2 = torch.zeros(int(bad_ptr[-1]), dtype=torch.float64, device=dev)
+    assert L.femb200_csr_pack_rows_async(ra.h, rows.size, _dev(t_rows), _dev(t_bad), _dev(oi2), _dev(ov2), _dev(mism)) == 0
+    assert L.femb200_sync(ra.ctx) == 0
+    assert int(mism.item()) == rows.size
+    mism.zero_()
+    oi[0] = int(ix.max()) + 7            # a column that no row holds
+    assert L.femb200_csr_add_entries_async(ra.h, rows.size, _dev(t_rows), _dev(t_ptr), _dev(oi), _dev(ov), _dev(mism)) == 0
+    assert L.femb200_sync(ra.ctx) == 0
+    assert int(mism.item()) == 1
+    ra.close()
+
+
+def test_column_map_and_node_mask(pkg, O, meshes):
+    """Rank-local numbering: an assembler over a subset of the nodes (ascending global ids) with a column map produces the
+    corresponding rows of the global K with GLOBAL column ids; a node mask restricts the assembled rows."""
+    import torch
+    nodes, conn = meshes.mesh_for("hexa8", 4)
+    Cm, bk = O.constitutive(0, 200e9, 0.3)
+    og = O.GeneralAssembler(nodes, 7)
+    og.add_isoparametric(O.HEXA8 if hasattr(O, "HEXA8") else KINDS["hexa8"]["kind"], Cm, bk, conn)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    sel = np.arange(conn.shape[0] // 3, conn.shape[0])               # a chunk of the elements
+    l2g = np.unique(conn[sel])
+    lconn = np.searchsorted(l2g, conn[sel]).astype(np.int32)
+    # rows whose node is touched ONLY by the selected elements are complete in the local K
+    others = np.setdiff1d(np.arange(conn.shape[0]), sel)
+    complete = ~np.isin(l2g, np.unique(conn[others]))
+    dev = torch.device("cuda", 0)
+    ra = pkg.RawAssembler(np.ascontiguousarray(nodes[l2g]), 3)
+    d_l2g = torch.from_numpy(l2g.astype(np.int32)).to(dev)
+    mask = torch.from_numpy(complete.astype(np.uint8)).to(dev)
+    L = pkg.lib()
+    assert L.femb200_assembler_set_column_map_device(ra.h, _dev(d_l2g), nodes.shape[0]) == 0
+    L.femb200_assembler_set_node_mask_device(ra.h, _dev(mask))
+    desc = ra.make_desc(pkg.elements.Hexa8(), pkg.solids.Isotropic(200e9, 0.3).Solid3D())
+    assert ra.add(desc, conn=lconn) == 0
+    ip, ix, v = ra.csr()
+    assert complete.any() and (~complete).any()
+    for ln_, gnode in enumerate(l2g):
+        for k in range(3):
+            lo, hi = ip[3 * ln_ + k], ip[3 * ln_ + k + 1]
+            if not complete[ln_]:
+                assert hi == lo                                               # masked out
+                continue
+            g = 3 * gnode + k
+            assert np.array_equal(ix[lo:hi], ri[rp[g]:rp[g + 1]])              # global column ids, bit-exact pattern
+            assert np.all(np.abs(v[lo:hi] - rv[rp[g]:rp[g + 1]]) <= TOL * np.maximum(np.abs(rv[rp[g]:rp[g + 1]]), ab[rp[g]:rp[g + 1]]))
+    ra.close()
+
+
 # ---- BASELINE config 1 at full size: size-independent properties ----------------------------------------
 def test_config1_full_size_properties(pkg, O, meshes):
     """Tetra4 BCC N=48: 1,299,456 elements / 684,723 dofs (benchmark_test.go largest case).  The oracle is
