@@ -14,6 +14,7 @@
 //   scan(rowlen) -> blkptr;  expand -> indptr (int64), indices (int32)
 #include "common.cuh"
 #include <cub/cub.cuh>
+#include <type_traits>
 #include <cstring>
 
 namespace femb200 {
@@ -143,12 +144,12 @@ k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__
 //      (the element -> CSR-slot map), written with vector stores.
 // Rows with more than 32 incidences or more than CAP distinct columns are flagged (rowlen = -1) and redone
 // by the sorted-insert kernel k_row_pattern.
-template <int NN, int HS>
-__global__ void __launch_bounds__(256)
+template <int NN, int HS, int IPL, int TPB>
+__global__ void __launch_bounds__(TPB)
 k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__restrict__ n2e_t,
                     const int32_t *__restrict__ conn, int32_t *__restrict__ tmpcols, int64_t *__restrict__ rowlen,
-                    uint16_t *__restrict__ pos16, const uint8_t *__restrict__ node_mask) {
-  constexpr int G = 8, IPL = 4, MAXINC = G * IPL;
+                    uint16_t *__restrict__ pos16, const uint8_t *__restrict__ node_mask, int only_flagged) {
+  constexpr int G = 8, MAXINC = G * IPL; // IPL incidences per lane: rows with more than 8*IPL incidences take the fallback
   constexpr int CAP = HS * 3 / 4;
   constexpr int LOG = HS == 32 ? 5 : (HS == 64 ? 6 : 7);
   constexpr int GW = HS + HS + MAXINC + CAP; // 32-bit words of shared memory per group
@@ -160,6 +161,7 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   int32_t *ul = reinterpret_cast<int32_t *>(lst + MAXINC);
   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + tid) / G;
   if (I >= n_nodes) return;
+  if (only_flagged && rowlen[I] >= 0) return;                             // done by the previous (cheaper) pass
   if (node_mask && !node_mask[I]) { if (l == 0) rowlen[I] = 0; return; } // row not assembled on this rank
   const int gshift = (tid & 31) & ~(G - 1);
   const unsigned gmask = 0xffu << gshift;
@@ -383,12 +385,28 @@ static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *
   const bool no_hash = getenv("FEMB200_NO_HASH_PATTERN") != nullptr;
   if (!no_hash) {
     constexpr int HS = NN <= 4 ? 32 : (NN <= 8 ? 64 : 128);
-    constexpr int GW = HS + HS + 32 + HS * 3 / 4;
-    const int T = 256;
-    const size_t smem = (size_t)(T / 8) * GW * sizeof(int32_t);
-    FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(k_row_pattern_group<NN, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_row_pattern_group<NN, HS><<<grid_for(n_nodes * 8, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, node_mask);
-    ctx->launches++;
+    // incidences per lane and block size.  Every incidence keeps nn connectivity entries in registers, so large elements
+    // run a first pass with ONE incidence per lane (rows with <= 8 incident elements: every node of a structured
+    // hexahedral grid, the mid-edge nodes of quadratic tetrahedra) in small blocks, and a second pass with four per lane
+    // only over the rows the first one flagged (vertex nodes of tetrahedral meshes: ~24 incident elements).
+    constexpr int T = NN >= 8 ? 128 : 256;
+    auto launch = [&](auto ipl_c, int only_flagged) -> int {
+      constexpr int IPL = decltype(ipl_c)::value;
+      constexpr int GW = HS + HS + 8 * IPL + HS * 3 / 4;
+      const size_t smem = (size_t)(T / 8) * GW * sizeof(int32_t);
+      auto kern = k_row_pattern_group<NN, HS, IPL, T>;
+      FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid_for(n_nodes * 8, T), T, smem, ctx->stream>>>(n_nodes, n2e_ptr, n2e_t, conn, tmpcols, rowlen, pos16, node_mask, only_flagged);
+      ctx->launches++;
+      return 0;
+    };
+    int rc;
+    if constexpr (NN >= 8) {
+      if ((rc = launch(std::integral_constant<int, 1>{}, 0))) return rc;
+      if ((rc = launch(std::integral_constant<int, 4>{}, 1))) return rc;
+    } else {
+      if ((rc = launch(std::integral_constant<int, 4>{}, 0))) return rc;
+    }
   }
   const int T = 128;
   // sorted-insert fallback: every row when the group path is disabled, else only the rows it flagged
