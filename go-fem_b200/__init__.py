@@ -69,6 +69,7 @@ def lib():
     L.femb200_csr_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.femb200_csr_at.argtypes = [vp, C.c_int64, C.c_int64, _dp]
     L.femb200_csr_matvec.argtypes = [vp, _dp, _dp]
+    L.femb200_csr_slice.argtypes = [vp, C.c_int64, _i64p, C.c_int64, _i64p, _i64p, _i32p, _dp, _i64p]
     L.femb200_csr_accumulate_rows_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
     L.femb200_csr_keep_rows_device.argtypes = [vp, vp]
     L.femb200_assembler_set_node_mask_device.argtypes = [vp, vp]
@@ -122,6 +123,24 @@ def exported_symbols():
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names += re.findall(r"\b((?:femb200|gofem)_\w+)\s*\(", src)
     return sorted(set(names))
+
+
+def _csr_slice(handle, rows, cols):
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    nnz = C.c_int64(0)
+    L = lib()
+    rp, cp = rows.ctypes.data_as(_i64p), cols.ctypes.data_as(_i64p)
+    rc = L.femb200_csr_slice(handle, rows.size, rp, cols.size, cp, None, None, None, C.byref(nnz))
+    if rc:
+        raise RuntimeError(f"femb200_csr_slice -> {rc}")
+    indptr = np.zeros(rows.size + 1, dtype=np.int64)
+    indices = np.zeros(nnz.value, dtype=np.int32)
+    values = np.zeros(nnz.value, dtype=np.float64)
+    rc = L.femb200_csr_slice(handle, rows.size, rp, cols.size, cp, indptr.ctypes.data_as(_i64p), indices.ctypes.data_as(_i32p), _d(values), C.byref(nnz))
+    if rc:
+        raise RuntimeError(f"femb200_csr_slice -> {rc}")
+    return indptr, indices, values
 
 
 def _d(a):
@@ -302,6 +321,11 @@ class Sparse:
             K[r, indices[indptr[r]:indptr[r + 1]]] = values[indptr[r]:indptr[r + 1]]
         return K
 
+    def Slice(self, rows, cols):
+        """lap.Slice(K, rows, cols) on the device (femb200_csr_slice): CSR (indptr, indices, values) of K[rows][:, cols]
+        with column indices = positions in `cols` (ascending, unique)."""
+        return _csr_slice(lib().gofem_device_assembler(self._ga._h), rows, cols)
+
     def MulVec(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.zeros_like(x)
@@ -475,6 +499,9 @@ class RawAssembler:
         k, e, q = C.c_int32(), C.c_int64(), C.c_int32()
         lib().femb200_last_error(self.h, C.byref(k), C.byref(e), C.byref(q))
         return k.value, e.value, q.value
+
+    def slice(self, rows, cols):
+        return _csr_slice(self.h, rows, cols)
 
     def reassemble(self, desc, nodes=None, nodes_device_ptr=None):
         """Numeric-only re-assembly on the cached pattern (femb200_reassemble)."""

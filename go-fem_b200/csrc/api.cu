@@ -414,6 +414,19 @@ int femb200_csr_at(const femb200_assembler *ga, int64_t i, int64_t j, double *ou
   return 0;
 }
 
+int femb200_csr_slice(const femb200_assembler *cga, int64_t n_rows, const int64_t *rows, int64_t n_cols, const int64_t *cols,
+                      int64_t *indptr, int32_t *indices, double *values, int64_t *nnz) {
+  femb200_assembler *ga = const_cast<femb200_assembler *>(cga);
+  if (!ga || n_rows < 0 || n_cols < 0 || (n_rows > 0 && !rows) || (n_cols > 0 && !cols)) return FEMB200_ERR_BAD_ARG;
+  for (int64_t i = 0; i < n_rows; ++i)
+    if (rows[i] < 0 || rows[i] >= ga->K.n_rows) return FEMB200_ERR_BAD_ARG;
+  for (int64_t i = 0; i < n_cols; ++i)
+    if (cols[i] < 0 || cols[i] >= ga->K.n_rows || (i > 0 && cols[i] <= cols[i - 1])) return FEMB200_ERR_BAD_ARG; // ascending, unique
+  if (ga->d_col_map) return FEMB200_ERR_UNSUPPORTED; // rank-local assemblers hold global column ids
+  FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
+  return csr_slice(ga, n_rows, rows, n_cols, cols, indptr, indices, values, nnz);
+}
+
 int femb200_csr_matvec(const femb200_assembler *cga, const double *x, double *y) {
   femb200_assembler *ga = const_cast<femb200_assembler *>(cga);
   if (!ga || !x || !y) return FEMB200_ERR_BAD_ARG;

@@ -208,5 +208,7 @@ int narrow_and_validate_conn(femb200_assembler *ga, const void *d_conn_in, bool 
                              int32_t *conn32_out);
 int slot_map(femb200_assembler *ga, int64_t *d_slot);
 int probe_peaks(femb200_ctx *ctx, int reps, double out[2]);
+int csr_slice(femb200_assembler *ga, int64_t n_rows, const int64_t *h_rows, int64_t n_cols, const int64_t *h_cols, int64_t *h_indptr,
+              int32_t *h_indices, double *h_values, int64_t *nnz_out);
 
 } // namespace femb200

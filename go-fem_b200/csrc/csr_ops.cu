@@ -364,4 +364,90 @@ int probe_peaks(femb200_ctx *ctx, int reps, double out[2]) {
   return 0;
 }
 
+
+// ---- K(rows, cols) extraction (lap.Slice(K, free, free) of the patch tests; Fixity.FreeDofs / FixedDofs) -------------
+__global__ void k_slice_colmap(int64_t n_cols, const int64_t *__restrict__ cols, int32_t *__restrict__ colmap) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_cols) colmap[cols[c]] = (int32_t)c;
+}
+// 8 lanes per selected row: count (fill == 0) or write (fill == 1) the entries whose column is selected
+__global__ void k_slice_rows(int64_t n_rows, const int64_t *__restrict__ rows, const int32_t *__restrict__ colmap,
+                             const int64_t *__restrict__ kptr, const int32_t *__restrict__ kidx, const double *__restrict__ kval,
+                             int64_t *__restrict__ cnt, const int64_t *__restrict__ optr, int32_t *__restrict__ oidx,
+                             double *__restrict__ oval, int fill) {
+  const int l = threadIdx.x & 7;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (w >= n_rows) return;
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+  const int64_t r = rows[w];
+  const int64_t lo = kptr[r], hi = kptr[r + 1];
+  int64_t base = fill ? optr[w] : 0;
+  int64_t total = 0;
+  for (int64_t k0 = lo; k0 < hi; k0 += 8) { // ordered compaction: ballot + popc keeps the columns ascending
+    const int64_t k = k0 + l;
+    const int32_t nc = k < hi ? colmap[kidx[k]] : -1;
+    const unsigned bal = (__ballot_sync(gmask, nc >= 0) >> ((threadIdx.x & 31) & ~7)) & 0xffu;
+    if (fill && nc >= 0) {
+      const int64_t o = base + __popc(bal & ((1u << l) - 1u));
+      oidx[o] = nc;
+      oval[o] = kval[k];
+    }
+    base += __popc(bal);
+    total += __popc(bal);
+  }
+  if (!fill && l == 0) cnt[w] = total;
+}
+
+int csr_slice(femb200_assembler *ga, int64_t n_rows, const int64_t *h_rows, int64_t n_cols, const int64_t *h_cols, int64_t *h_indptr,
+              int32_t *h_indices, double *h_values, int64_t *nnz_out) {
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  const DeviceCsr &K = ga->K;
+  ScratchScope scope(ctx);
+  int64_t *d_rows = nullptr, *d_cols = nullptr, *cnt = nullptr, *optr = nullptr;
+  int32_t *colmap = nullptr;
+  int rc;
+  if ((rc = scratch_alloc(ctx, &d_rows, n_rows))) return rc;
+  if ((rc = scratch_alloc(ctx, &d_cols, n_cols))) return rc;
+  if ((rc = scratch_alloc(ctx, &cnt, n_rows + 1))) return rc;
+  if ((rc = scratch_alloc(ctx, &optr, n_rows + 1))) return rc;
+  if ((rc = scratch_alloc(ctx, &colmap, K.n_rows))) return rc;
+  if (n_rows) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_rows, h_rows, sizeof(int64_t) * n_rows, cudaMemcpyHostToDevice, st));
+  if (n_cols) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_cols, h_cols, sizeof(int64_t) * n_cols, cudaMemcpyHostToDevice, st));
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(colmap, 0xff, sizeof(int32_t) * (K.n_rows ? K.n_rows : 1), st));
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, sizeof(int64_t) * (n_rows + 1), st));
+  if (n_cols) k_slice_colmap<<<grid_for(n_cols, 256), 256, 0, st>>>(n_cols, d_cols, colmap);
+  if (n_rows && K.nnz)
+    k_slice_rows<<<grid_for(n_rows * 8, 256), 256, 0, st>>>(n_rows, d_rows, colmap, K.indptr, K.indices, K.values, cnt, nullptr, nullptr, nullptr, 0);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, cnt, optr, (int)(n_rows + 1), st);
+  if (need > ctx->cub_tmp_bytes) {
+    if (ctx->cub_tmp) cudaFreeAsync(ctx->cub_tmp, st);
+    ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
+    FEMB_CUDA_OK(ctx, cudaMallocAsync(&ctx->cub_tmp, need + 256, ctx->pool, st));
+    ctx->cub_tmp_bytes = need + 256;
+  }
+  size_t tb = ctx->cub_tmp_bytes;
+  FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, cnt, optr, (int)(n_rows + 1), st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, optr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  const int64_t nnz = ctx->h_scalars[0];
+  ctx->launches += 4;
+  if (nnz_out) *nnz_out = nnz;
+  if (!h_indptr && !h_indices && !h_values) return 0; // size query
+  int32_t *oidx = nullptr;
+  double *oval = nullptr;
+  if ((rc = scratch_alloc(ctx, &oidx, nnz))) return rc;
+  if ((rc = scratch_alloc(ctx, &oval, nnz))) return rc;
+  if (n_rows && K.nnz) {
+    k_slice_rows<<<grid_for(n_rows * 8, 256), 256, 0, st>>>(n_rows, d_rows, colmap, K.indptr, K.indices, K.values, cnt, optr, oidx, oval, 1);
+    ctx->launches++;
+  }
+  if (h_indptr) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(h_indptr, optr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyDeviceToHost, st));
+  if (h_indices && nnz) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(h_indices, oidx, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, st));
+  if (h_values && nnz) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(h_values, oval, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
 } // namespace femb200

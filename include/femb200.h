@@ -183,6 +183,14 @@ int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc
                                   const void *conn, int32_t conn_is_int64, int32_t conn_on_device,
                                   int64_t n_elem, const double *u, double *strains);
 
+/* lap.Slice(K, rows, cols) (constitution/solids/patch_test.go:80,87: K(free,free), K(free,fixed) from fem.Fixity's
+ * FreeDofs / FixedDofs, fem.go:175-232), extracted on the device: the selected rows of K restricted to the selected
+ * columns, as a CSR whose column indices are positions in `cols` (cols ascending and unique; rows in any order).
+ * Two-call pattern: with indptr = indices = values = NULL only *nnz is written; then indptr[n_rows+1], indices[nnz],
+ * values[nnz] (host arrays) are filled. */
+int femb200_csr_slice(const femb200_assembler *ga, int64_t n_rows, const int64_t *rows, int64_t n_cols, const int64_t *cols,
+                      int64_t *indptr, int32_t *indices, double *values, int64_t *nnz);
+
 /* Device-side phase timers of the last add call, milliseconds (CUDA events on the context stream):
  * [0] upload+validate [1] node->element adjacency [2] row pattern [3] CSR expand
  * [4] numeric + row reduction [5] merge into K [6] total device [7] numeric kernel launches in total

@@ -562,6 +562,31 @@ def test_column_map_and_node_mask(pkg, O, meshes):
     ra.close()
 
 
+def test_csr_slice_free_fixed(pkg, meshes):
+    """K(free,free) / K(free,fixed) extraction on the device (lap.Slice in patch_test.go:80,87 with Fixity's dof lists)."""
+    import scipy.sparse as sp
+    nodes, conn = meshes.mesh_for("hexa8", 5)
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    assert ga.AddIsoparametricFlat(pkg.elements.Hexa8(), pkg.solids.Isotropic(200e9, 0.3).Solid3D(), conn) is None
+    K = ga.Ksolid()
+    ip, ix, v = K.csr()
+    n = ip.size - 1
+    A = sp.csr_matrix((v, ix, ip), shape=(n, n))
+    fix = pkg.fem.NewFixity(7, nodes.shape[0])
+    for node in np.nonzero(nodes[:, 0] < 1e-9)[0]:
+        fix.Fix(int(node), 7)
+    fix.Fix(int(nodes.shape[0] - 1), 2)
+    free, fixed = np.array(fix.FreeDofs()), np.array(fix.FixedDofs())
+    assert free.size + fixed.size == n and fixed.size > 0
+    for rows, cols in ((free, free), (free, fixed), (fixed[::-1].copy(), free), (free[:0], free), (free, fixed[:0])):
+        p, i, x = K.Slice(rows, cols)
+        ref = A[rows][:, cols].tocsr()
+        ref.sort_indices()
+        assert np.array_equal(p, ref.indptr) and np.array_equal(i, ref.indices) and np.array_equal(x, ref.data)
+    with pytest.raises(RuntimeError):
+        K.Slice(free, fixed[::-1].copy())          # columns must be ascending
+
+
 # ---- BASELINE config 1 at full size: size-independent properties ----------------------------------------
 def test_config1_full_size_properties(pkg, O, meshes):
     """Tetra4 BCC N=48: 1,299,456 elements / 684,723 dofs (benchmark_test.go largest case).  The oracle is
