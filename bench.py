@@ -12,8 +12,9 @@ solids.Isotropic{E:200e9, Poisson:0.3}.Solid3D().
           on the library's stream, L2 flushed between steps.
   e2e   : the same through the reference-facing host API with HOST buffers (pinned): H2D of nodes and int64
           connectivity, assembly, D2H of the full CSR K into pinned host arrays, all inside the timed region.
-  roofline     : dominant kernel (k_numeric_rows: numeric phase fused with the row reduction) against the
-                 measured HBM copy bandwidth of MEASURED_PEAKS.json.
+  roofline     : dominant kernel (k_noderows: B^T C B products fused with the deterministic row reduction) against the
+                 measured HBM copy bandwidth of MEASURED_PEAKS.json; FP64 / copy peaks probed in the same process.
+  reassemble_cached_pattern : numeric-only re-assembly on the cached symbolic plan (femb200_reassemble).
   cpu_baseline : the CPU oracle (C port of the reference algorithm, single thread like the reference) timed on
                  this box's host cores on the same workload.
   --impl reference : the oracle port timed alone (the Go reference cannot be built: no Go toolchain).
