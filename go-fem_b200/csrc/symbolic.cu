@@ -373,14 +373,15 @@ __global__ void k_indptr(int64_t n_nodes, int mdpn, int nu, unsigned umask, cons
 // One warp per node row: expands the ascending column-node list of the row into the nu scalar CSR rows of the node.
 // The nu*nu*rl column indices of a node are contiguous in `indices` (scalar row ur at offset ur*rl*nu), so lane l
 // writes entries l, l+32, ...: fully coalesced 128-byte stores, the column nodes come from L1.
-template <int NU>
+// LPN lanes per node row: a warp for long rows, 8 lanes when every scalar row fits 32 entries (2-D meshes).
+template <int NU, int LPN>
 __global__ void __launch_bounds__(256)
 k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ umap_packed, const int32_t *__restrict__ n2e_ptr,
          const int64_t *__restrict__ blkptr, const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices,
          const int32_t *__restrict__ col_map) {
   const int nu = NU > 0 ? NU : nu_rt;
-  const int lane = threadIdx.x & 31;
-  const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & (LPN - 1);
+  const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPN;
   if (I >= n_nodes) return;
   const int64_t b0 = blkptr[I];
   const int rl = (int)(blkptr[I + 1] - b0);
@@ -391,7 +392,7 @@ k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ u
 #pragma unroll
   for (int u = 0; u < (NU > 0 ? NU : kMaxNdn); ++u) um[u] = u < nu ? umap_packed[u] : 0;
   int32_t *out = indices + (int64_t)nu * nu * b0;
-  for (int idx = lane; idx < rowsz; idx += 32) {
+  for (int idx = lane; idx < rowsz; idx += LPN) {
     const int p = idx / nu, uc = idx - p * nu;
     int off = um[0];
 #pragma unroll
@@ -565,13 +566,20 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   k_indptr<<<grid_for(ndof + 1, 256), 256, 0, st>>>(n_nodes, sh.mdpn, nu, umask, out->blkptr, out->csr.indptr);
   ctx->launches++;
   if (out->nblk) {
-    const unsigned eg = grid_for(n_nodes * 32, 256);
+    const bool small = (int64_t)out->max_rowlen * nu <= 32;       // short rows: 8 lanes per node row, 4 rows per warp
+    const unsigned eg = grid_for(n_nodes * (small ? 8 : 32), 256);
+#define FEMB_EXPAND(NUV)                                                                                                          \
+  do {                                                                                                                          \
+    if (small) k_expand<NUV, 8><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); \
+    else k_expand<NUV, 32><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map);   \
+  } while (0)
     switch (nu) {
-    case 1: k_expand<1><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
-    case 2: k_expand<2><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
-    case 3: k_expand<3><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
-    default: k_expand<0><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); break;
+    case 1: FEMB_EXPAND(1); break;
+    case 2: FEMB_EXPAND(2); break;
+    case 3: FEMB_EXPAND(3); break;
+    default: FEMB_EXPAND(0); break;
     }
+#undef FEMB_EXPAND
     ctx->launches++;
   }
   FEMB_CUDA_OK(ctx, cudaGetLastError());
