@@ -402,7 +402,7 @@ __device__ __forceinline__ void st256(double *p, double a, double b, double c, d
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int D, int NN, int BKIND, bool TAB_CONST>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (NN <= 4 && D == 3 ? 6 : 1)) // linear tetrahedra: 75 registers, 6 blocks per SM (store bound)
 k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__restrict__ conn, double *__restrict__ stag,
            uint8_t *__restrict__ degen, unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp) {
   using B = BT<BKIND, D>;
