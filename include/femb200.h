@@ -114,13 +114,14 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
 
 /* After a non-zero status: which error, the lowest failing element index and its first failing
  * quadrature point (-1 when not applicable). */
+int femb200_last_error(const femb200_assembler *ga, int32_t *kind, int64_t *elem, int32_t *qp);
+
 /* Numeric-only re-assembly on the cached pattern (the reference rebuilds everything on every call):
  * recomputes the values of K for the connectivity of the ONE AddIsoparametric call this assembler has committed, with a
  * new descriptor (material, quadrature order, tables; same element shape) and optionally new node coordinates
  * (n_nodes x 3, NULL = keep).  The symbolic phase is skipped: geometry kernel + node-row kernel only.  Same error
  * semantics as femb200_add_isoparametric (K untouched on error).  FEMB200_ERR_BAD_ARG if more than one call was merged. */
 int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, const double *nodes, int32_t nodes_on_device);
-int femb200_last_error(const femb200_assembler *ga, int32_t *kind, int64_t *elem, int32_t *qp);
 
 /* (*GeneralAssembler).TotalDofs (assembler.go:34-37) and the size of Ksolid() (assembler.go:31). */
 int64_t femb200_total_dofs(const femb200_assembler *ga);
@@ -134,7 +135,8 @@ int femb200_csr_device(const femb200_assembler *ga, const int64_t **indptr, cons
                        const double **values);
 /* lap.Sparse.At(i,j) (call sites example_test.go:38, patch_test.go:80): one entry, 0 if absent. */
 int femb200_csr_at(const femb200_assembler *ga, int64_t i, int64_t j, double *out);
-/* K*x on the device, x and y on the host (forces.MulVec(K,u), patch_test.go:92). */
+/* K*x on the device, x and y on the host (forces.MulVec(K,u), patch_test.go:92).  (Assemblers with a column map hold
+ * global column ids over local rows: femb200_csr_at / _matvec / _slice address K by its own row numbering only.) */
 int femb200_csr_matvec(const femb200_assembler *ga, const double *x, double *y);
 
 /* ---- multi-GPU row-block exchange (one process per GPU; the collective itself is NCCL all-to-all driven by
