@@ -119,3 +119,23 @@ def test_mesh_generators(meshes, O):
         ga = O.GeneralAssembler(nodes, flags)
         ga.add_isoparametric(k, C, bk, conn)
         assert ga.csr()[2].size > 0
+
+
+def test_go_shim_binds_only_declared_symbols(pkg):
+    """The (uncompiled: no Go toolchain in the image) cgo shim under go-fem_b200/gofem may only call entry points that
+    include/femb200.h declares and libfemb200.so exports, and it must bind the hot-path entry points."""
+    import os
+    import re
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set(pkg.exported_symbols())
+    used = set()
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "go-fem_b200", "gofem")):
+        for f in files:
+            if f.endswith(".go"):
+                used |= set(re.findall(r"\bC\.(femb200_\w+)\(", open(os.path.join(dirpath, f)).read()))
+    assert used, "no cgo calls found"
+    assert used <= declared, sorted(used - declared)
+    for must in ("femb200_ctx_create", "femb200_assembler_create", "femb200_add_isoparametric", "femb200_last_error", "femb200_csr_copy",
+                 "femb200_nnz", "femb200_total_dofs", "femb200_reassemble"):
+        assert must in used, must
+
