@@ -235,8 +235,8 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
     cudaError_t e = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
   }
+  if (!rc && cudaEventRecord(ctx->ev[1], st) != cudaSuccess) { ctx->last_cuda_error = "cudaEventRecord"; rc = FEMB200_ERR_CUDA; }
   if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; return rc; }
-  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], st));
 
   rc = symbolic_phase(ga, sh, conn32, n_elem, &sym); // synchronises once (nblk, max row length, error word)
   if (rc == -1) rc = decode_error(ga);
@@ -259,6 +259,7 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   ga->plan.conn32 = conn32; conn32 = nullptr;
   ga->plan.order = sym.order; ga->plan.n_short = sym.n_short;
   ga->plan.n_numeric = n_elem - n_pattern_only;
+  ga->plan.nblk = sym.nblk;
   ga->plan.d = sh.d; ga->plan.ndn = sh.ndn; ga->plan.bkind = sh.bkind; ga->plan.max_rowlen = sym.max_rowlen; ga->plan.identity = sh.identity;
   for (int s = 0; s < 4; ++s) ga->plan.group_need[s] = sym.group_need[s];
   ga->plan.matches_K = (ga->K.nnz == 0);
@@ -287,6 +288,7 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
   FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   LastPlan &pl = ga->plan;
   if (!pl.conn32 || !pl.matches_K || ga->K.nnz == 0) return FEMB200_ERR_BAD_ARG; // exactly one committed call on this assembler
+  if (ga->K.nnz != (int64_t)pl.nu * pl.nu * pl.nblk) return FEMB200_ERR_BAD_ARG;   // K was reshaped behind the plan's back
   ga->err_kind = 0; ga->err_elem = -1; ga->err_qp = -1;
   ElemShape sh;
   std::vector<double> blob;
@@ -308,7 +310,8 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
       ga->own_nodes = false;
     } else {
       if ((rc = dev_alloc(ctx, &fresh_nodes, (size_t)ga->n_nodes * 3))) return rc;
-      FEMB_CUDA_OK(ctx, cudaMemcpyAsync(fresh_nodes, nodes, sizeof(double) * 3 * ga->n_nodes, cudaMemcpyHostToDevice, st));
+      cudaError_t e = cudaMemcpyAsync(fresh_nodes, nodes, sizeof(double) * 3 * ga->n_nodes, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); dev_free(ctx, fresh_nodes); return FEMB200_ERR_CUDA; }
       ga->d_nodes = fresh_nodes;
       ga->own_nodes = true;
     }
@@ -318,13 +321,24 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
     ga->d_nodes = old_nodes;
     ga->own_nodes = old_own;
   };
-  *ctx->h_err = kNoError;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
-  ScratchScope scratch_scope(ctx);
+  // from here on the assembler is mutated (node pointer swapped): every failure leaves through fail(), which frees the
+  // temporaries and restores the old coordinates, so that a failed re-assembly leaves the assembler exactly as it was
   double *d_tab = nullptr, *newvals = nullptr;
-  if ((rc = scratch_alloc(ctx, &d_tab, blob.size()))) return rc;
-  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st));
-  if ((rc = dev_alloc(ctx, &newvals, (size_t)ga->K.nnz))) return rc;
+  ScratchScope scratch_scope(ctx);
+  auto fail = [&](int code, cudaError_t ce = cudaSuccess) {
+    if (ce != cudaSuccess) ctx->last_cuda_error = cudaGetErrorString(ce);
+    dev_free(ctx, newvals);
+    restore_nodes();
+    ga->err_kind = code;
+    cudaStreamSynchronize(st);
+    return code;
+  };
+  cudaError_t ce;
+  *ctx->h_err = kNoError;
+  if ((ce = cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st)) != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
+  if ((rc = scratch_alloc(ctx, &d_tab, blob.size()))) return fail(rc);
+  if ((ce = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
+  if ((rc = dev_alloc(ctx, &newvals, (size_t)ga->K.nnz))) return fail(rc);
   SymbolicResult sym;
   sym.n2e_ptr = pl.n2e_ptr; sym.n2e_t = pl.n2e_t; sym.pos16 = pl.pos16; sym.blkptr = pl.blkptr;
   sym.max_rowlen = pl.max_rowlen;
@@ -332,16 +346,16 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
   for (int s = 0; s < 4; ++s) sym.group_need[s] = pl.group_need[s];
   sym.csr.n_rows = ga->K.n_rows; sym.csr.nnz = ga->K.nnz; sym.csr.indptr = ga->K.indptr; sym.csr.indices = ga->K.indices;
   sym.csr.values = newvals;
-  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
+  if ((ce = cudaEventRecord(ctx->ev[4], st)) != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
   rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), pl.conn32, pl.n_numeric, &sym);
   if (!rc) {
-    cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
+    ce = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev[5], st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
   }
   if (!rc) rc = decode_error(ga);
-  if (rc) { dev_free(ctx, newvals); restore_nodes(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; } // K untouched
+  if (rc) return fail(rc); // K untouched
   if (nodes && old_own) { double *d = const_cast<double *>(old_nodes); dev_free(ctx, d); }
   dev_free(ctx, ga->K.values);
   ga->K.values = newvals;

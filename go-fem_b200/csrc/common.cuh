@@ -57,6 +57,7 @@ struct LastPlan {
   int32_t *order = nullptr;     // two-class visiting order (see SymbolicResult), or NULL
   int64_t n_short = 0;
   int64_t n_numeric = 0;        // elements [n_numeric, n_elem) are pattern-only
+  int64_t nblk = 0;             // node blocks of this call's pattern: K.nnz must equal nu*nu*nblk while matches_K holds
   int d = 0, ndn = 0, bkind = 0, max_rowlen = 0;
   int64_t group_need[4] = {0, 0, 0, 0};
   bool identity = false;
@@ -182,6 +183,8 @@ struct SymbolicResult {
   int32_t *order = nullptr;   // two-class visiting order of the node rows (short rows first), or NULL
   int64_t n_short = 0;        // rows [0, n_short) of `order` have rowlen <= max_rowlen / 2
   int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive rows of sum(rowlen)
+  const int32_t *rowcols = nullptr; // ascending column nodes of row I at rowcols[cols_stride * n2e_ptr[I] ...] (call scratch)
+  int cols_stride = 0;
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)
 };
 

@@ -82,6 +82,7 @@ int csr_merge_into(femb200_assembler *ga, DeviceCsr *add) {
   dev_free(ctx, add->indptr); dev_free(ctx, add->indices); dev_free(ctx, add->values);
   *add = DeviceCsr();
   K = out;
+  ga->plan.matches_K = false; // K's pattern is now a union: the cached symbolic plan no longer addresses its slots
   return 0;
 }
 
@@ -126,6 +127,7 @@ int csr_accumulate_rows(femb200_assembler *ga, int64_t n_rows, const int64_t *ro
   ctx->launches += 3;
   dev_free(ctx, len);
   if (ga->K.nnz == 0 && add.nnz == 0) { dev_free(ctx, add.indptr); dev_free(ctx, add.indices); dev_free(ctx, add.values); return 0; }
+  ga->plan.matches_K = false; // foreign rows enter K (also when K was empty and simply adopts them)
   return csr_merge_into(ga, &add);
 }
 
@@ -280,6 +282,7 @@ int csr_keep_rows(femb200_assembler *ga, const uint8_t *keep) {
   dev_free(ctx, len);
   dev_free(ctx, K.indptr); dev_free(ctx, K.indices); dev_free(ctx, K.values);
   K = out;
+  ga->plan.matches_K = false; // rows were dropped: the plan's block offsets are stale
   return 0;
 }
 

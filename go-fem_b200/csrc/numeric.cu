@@ -13,242 +13,11 @@
 // No COO stream, no Ke staging in HBM, no atomics: every K entry is a fixed-order (ascending element)
 // sum, i.e. a deterministic segmented reduction whose segments are the CSR rows.  HBM traffic is the
 // compulsory one: connectivity + coordinates (L2 resident) in, CSR values out.
-#include "common.cuh"
-#include <type_traits>
+#include "numeric.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace femb200 {
-
-__constant__ double c_tab[kTabDoubles];
-
-// ---- strain-displacement block structure ---------------------------------------------------------
-// Node "values" v[] and the selector sel(k,i): B_node[k][i] = v[sel] (or 0 when sel < 0).
-//  XYZ            v = (gx, gy, gz)              straindisplacement.go:5-26
-//  PLANE          v = (gx, gy)                  straindisplacement.go:28-40
-//  AXISYM         v = (gr, gz, N/r)             straindisplacement.go:42-58
-//  THERMAL        v = (g0..g_{d-1})             thermal.go:18-21,31-34 (B = dN)
-//  THERMAL_AXISYM v = (N/r + gr, gz)            thermal.go:43-56
-template <int BKIND, int D> struct BT;
-template <> struct BT<FEMB200_B_XYZ, 3> {
-  static constexpr int NDN = 3, DIMC = 6, NV = 3; static constexpr bool RADIAL = false;
-  __host__ __device__ static constexpr int sel(int k, int i) {
-    constexpr int t[6][3] = {{0, -1, -1}, {-1, 1, -1}, {-1, -1, 2}, {1, 0, -1}, {-1, 2, 1}, {2, -1, 0}};
-    return t[k][i];
-  }
-};
-template <> struct BT<FEMB200_B_PLANE, 2> {
-  static constexpr int NDN = 2, DIMC = 3, NV = 2; static constexpr bool RADIAL = false;
-  __host__ __device__ static constexpr int sel(int k, int i) {
-    constexpr int t[3][2] = {{0, -1}, {-1, 1}, {1, 0}};
-    return t[k][i];
-  }
-};
-template <> struct BT<FEMB200_B_AXISYM, 2> {
-  static constexpr int NDN = 2, DIMC = 4, NV = 3; static constexpr bool RADIAL = true;
-  __host__ __device__ static constexpr int sel(int k, int i) {
-    constexpr int t[4][2] = {{0, -1}, {2, -1}, {-1, 1}, {1, 0}};
-    return t[k][i];
-  }
-};
-template <int D> struct BT<FEMB200_B_THERMAL, D> {
-  static constexpr int NDN = 1, DIMC = D, NV = D; static constexpr bool RADIAL = false;
-  __host__ __device__ static constexpr int sel(int k, int i) { return k; }
-};
-template <> struct BT<FEMB200_B_THERMAL_AXISYM, 2> {
-  static constexpr int NDN = 1, DIMC = 2, NV = 2; static constexpr bool RADIAL = true;
-  __host__ __device__ static constexpr int sel(int k, int i) { return k; }
-};
-
-// ---- table access: __constant__ (uniform broadcast) or global fallback for oversized tables -------
-template <bool TAB_CONST> struct Tab {
-  const double *g;
-  int offW, offN, offDN;
-  __device__ __forceinline__ double at(int i) const {
-    if constexpr (TAB_CONST) return c_tab[i]; else return __ldg(g + i);
-  }
-  template <int DIMC> __device__ __forceinline__ double C(int k, int c) const { return at(k * DIMC + c); }
-  __device__ __forceinline__ double w(int q) const { return at(offW + q); }
-  template <int NN> __device__ __forceinline__ double N(int q, int b) const { return at(offN + q * NN + b); }
-  template <int D, int NN> __device__ __forceinline__ double dN(int q, int i, int b) const { return at(offDN + (q * D + i) * NN + b); }
-};
-
-// ---- d x d determinant and inverse --------------------------------------------------------------
-// The determinant follows the reference's algorithm class: LU with partial pivoting (gonum mat.Det ->
-// Dgetf2, first-max pivot, multipliers = a * (1/pivot)), det = sign * prod(u_ii), so that exactly singular
-// Jacobians (collapsed elements: two identical rows) give EXACTLY 0 -> "zero determinant", and the
-// sign of a degenerate element is not decided by FMA rounding noise.  The inverse is the adjugate
-// scaled by 1/det (differences to the reference's LU solve are O(eps * cond)).
-template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D][D]) {
-  double A[D][D];
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int j = 0; j < D; ++j) A[i][j] = Jin[i][j];
-  double det = 1.0;
-#pragma unroll
-  for (int j = 0; j < D; ++j) {
-    // first index of the largest |A[i][j]|, i >= j; swap it into row j (predicated, static indices)
-    double best = fabs(A[j][j]);
-    int p = j;
-#pragma unroll
-    for (int i = j + 1; i < D; ++i) {
-      const double v = fabs(A[i][j]);
-      if (v > best) { best = v; p = i; }
-    }
-#pragma unroll
-    for (int i = j + 1; i < D; ++i)
-      if (p == i) {
-#pragma unroll
-        for (int k = 0; k < D; ++k) { const double t = A[j][k]; A[j][k] = A[i][k]; A[i][k] = t; }
-        det = -det;
-      }
-    const double piv = A[j][j];
-    det = __dmul_rn(det, piv);
-    if (piv != 0.0) {
-      const double r = 1.0 / piv;
-#pragma unroll
-      for (int i = j + 1; i < D; ++i) {
-        const double l = __dmul_rn(A[i][j], r);
-#pragma unroll
-        for (int k = j + 1; k < D; ++k) A[i][k] = __dsub_rn(A[i][k], __dmul_rn(l, A[j][k])); // no FMA: same rounding as the reference's LU
-      }
-    }
-  }
-  return det;
-}
-
-template <int D> __device__ __forceinline__ double inv_det(const double (&J)[D][D], double (&inv)[D][D]);
-template <> __device__ __forceinline__ double inv_det<1>(const double (&J)[1][1], double (&inv)[1][1]) {
-  inv[0][0] = 1.0 / J[0][0];
-  return J[0][0];
-}
-template <> __device__ __forceinline__ double inv_det<2>(const double (&J)[2][2], double (&inv)[2][2]) {
-  const double det = lu_det<2>(J);
-  const double r = 1.0 / det;
-  inv[0][0] = J[1][1] * r; inv[0][1] = -J[0][1] * r;
-  inv[1][0] = -J[1][0] * r; inv[1][1] = J[0][0] * r;
-  return det;
-}
-template <> __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&inv)[3][3]) {
-  const double det = lu_det<3>(J);
-  const double r = 1.0 / det;
-  inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * r;
-  inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * r;
-  inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * r;
-  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
-  inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
-  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
-  inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
-  inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
-  inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
-  return det;
-}
-template <int D> __device__ __forceinline__ double norm1(const double (&A)[D][D]) {
-  double m = 0;
-#pragma unroll
-  for (int j = 0; j < D; ++j) {
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < D; ++i) s += fabs(A[i][j]);
-    m = fmax(m, s);
-  }
-  return m;
-}
-
-// Geometry of one quadrature point.  Returns the error kind (0 = ok) exactly where the reference
-// would have returned it (assembler_isoparametric.go:95-107).
-template <int D, int NN, bool RADIAL, class TabT>
-__device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double (&X)[NN][D], double (&inv)[D][D],
-                                           double &detJ, double &rinv, double &scale) {
-  double J[D][D];
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int j = 0; j < D; ++j) J[i][j] = 0.0;
-#pragma unroll
-  for (int b = 0; b < NN; ++b)
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      const double dn = tab.template dN<D, NN>(q, i, b);
-#pragma unroll
-      for (int j = 0; j < D; ++j) J[i][j] = __dadd_rn(J[i][j], __dmul_rn(dn, X[b][j])); // jac.Mul(dN, X): node-ascending, unfused (:93)
-    }
-  detJ = inv_det<D>(J, inv);
-  if (detJ < 0) return FEMB200_ERR_NEG_DET;
-  if (detJ < 1e-12) return FEMB200_ERR_ZERO_DET;
-  if (norm1<D>(J) * norm1<D>(inv) > 1e16) return FEMB200_ERR_SOLVE;
-  scale = 1.0;
-  rinv = 0.0;
-  if constexpr (RADIAL) {
-    double r = 0.0;
-#pragma unroll
-    for (int b = 0; b < NN; ++b) r = fma(X[b][0], tab.template N<NN>(q, b), r);
-    rinv = 1.0 / r;
-    scale = r;
-    if (isnan(r)) return FEMB200_ERR_NAN_SCALE;
-  }
-  return 0;
-}
-
-// v[] of one node at quadrature point q (see BT above)
-template <int BKIND, int D, int NN, class TabT>
-__device__ __forceinline__ void node_vals(const TabT &tab, int q, int b, const double (&inv)[D][D], double rinv,
-                                          double (&v)[BT<BKIND, D>::NV]) {
-  double g[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) {
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) s = fma(inv[i][j], tab.template dN<D, NN>(q, j, b), s);
-    g[i] = s;
-  }
-  if constexpr (BKIND == FEMB200_B_AXISYM) {
-    v[0] = g[0]; v[1] = g[1]; v[2] = tab.template N<NN>(q, b) * rinv;
-  } else if constexpr (BKIND == FEMB200_B_THERMAL_AXISYM) {
-    v[0] = tab.template N<NN>(q, b) * rinv + g[0]; v[1] = g[1];
-  } else {
-#pragma unroll
-    for (int i = 0; i < D; ++i) v[i] = g[i];
-  }
-}
-
-// E = f * B_a^T C   (NDN x DIMC), only the structural non-zeros of B_a are touched
-template <int BKIND, int D, class TabT>
-__device__ __forceinline__ void bt_c(const TabT &tab, const double (&va)[BT<BKIND, D>::NV], double f,
-                                     double (&E)[BT<BKIND, D>::NDN][BT<BKIND, D>::DIMC]) {
-  using B = BT<BKIND, D>;
-  double vs[B::NV];
-#pragma unroll
-  for (int i = 0; i < B::NV; ++i) vs[i] = va[i] * f;
-#pragma unroll
-  for (int i = 0; i < B::NDN; ++i)
-#pragma unroll
-    for (int c = 0; c < B::DIMC; ++c) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < B::DIMC; ++k)
-        if (B::sel(k, i) >= 0) s = fma(vs[B::sel(k, i)], tab.template C<B::DIMC>(k, c), s);
-      E[i][c] = s;
-    }
-}
-
-// blk = E * B_b  (NDN x NDN)
-template <int BKIND, int D>
-__device__ __forceinline__ void e_b(const double (&E)[BT<BKIND, D>::NDN][BT<BKIND, D>::DIMC],
-                                    const double (&vb)[BT<BKIND, D>::NV],
-                                    double (&blk)[BT<BKIND, D>::NDN * BT<BKIND, D>::NDN]) {
-  using B = BT<BKIND, D>;
-#pragma unroll
-  for (int i = 0; i < B::NDN; ++i)
-#pragma unroll
-    for (int j = 0; j < B::NDN; ++j) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < B::DIMC; ++k)
-        if (B::sel(k, j) >= 0) s = fma(E[i][k], vb[B::sel(k, j)], s);
-      blk[i * B::NDN + j] = s;
-    }
-}
 
 struct NumArgs {
   int64_t n_nodes;
@@ -385,23 +154,10 @@ k_numeric_rows(const NumArgs a) {
 //  k_rows      -- deterministic row reduction fused with the B^T C B products (see the comment on the kernel).
 // =====================================================================================================
 
-template <int BKIND, int D, int NN> struct Stag {
-  using B = BT<BKIND, D>;
-  static constexpr bool FIN = (B::NV == 3);                 // f stored in every node's 4th slot
-  static constexpr int NVP = FIN ? 4 : B::NV;               // doubles per node
-  static constexpr int REC = FIN ? NN * 4 : ((NN * B::NV + 2) & ~1);
-  static constexpr int FOFF = NN * B::NV;                   // !FIN: position of f
-};
 
-__device__ __forceinline__ void ld256(const double *p, double (&v)[4]) {
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
-__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <int D, int NN, int BKIND, bool TAB_CONST>
+// STORE = false: the reference's per-element checks only (error word), nothing is staged -- the companion of the fused
+// scalar-row kernel (srows.cu), which recomputes the geometry it needs.
+template <int D, int NN, int BKIND, bool TAB_CONST, bool STORE = true>
 __global__ void __launch_bounds__(128, (NN <= 4 && D == 3 ? 6 : 1)) // linear tetrahedra: 75 registers, 6 blocks per SM (store bound)
 k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__restrict__ conn, double *__restrict__ stag,
            uint8_t *__restrict__ degen, unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp) {
@@ -431,16 +187,18 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
 #pragma unroll
     for (int j = 0; j < D; ++j) X[b][j] = __ldg(nodes + (int64_t)nid[b] * 3 + j);
   }
-  degen[e] = dup ? 1 : 0;
+  if constexpr (STORE) degen[e] = dup ? 1 : 0;
   for (int q = 0; q < nqp; ++q) {
     double inv[D][D], detJ, rinv, scale;
     const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
     double *rec = stag + (e * nqp + q) * REC;
     if (ek) {
       atomicMin(err, pack_error(e, q, ek));
-      for (int m = 0; m < REC; ++m) rec[m] = 0.0;
+      if constexpr (STORE)
+        for (int m = 0; m < REC; ++m) rec[m] = 0.0;
       return; // the reference stops at the first failing quadrature point of the element (:95-107)
     }
+    if constexpr (!STORE) continue;
     const double f = detJ * tab.w(q) * scale; // (dJac*w)*scale, left to right (:111)
     if constexpr (S::FIN) {
 #pragma unroll
@@ -466,22 +224,6 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
   }
 }
 
-struct RowArgs {
-  int64_t n_nodes;
-  int64_t n_numeric;          // elements [n_numeric, n_elem) are pattern-only (halo): no values
-  const int32_t *n2e_ptr;
-  const uint32_t *n2e_t;
-  const uint16_t *pos16;
-  const int64_t *blkptr;
-  const double *stag;
-  const uint8_t *degen;
-  const int32_t *order;       // visiting order of the node rows (NULL: identity)
-  int64_t v0, v1;             // visiting range of this launch
-  double *values;
-  int64_t ninc;               // n_elem * nn (length of n2e_t)
-  int nqp;
-  double C[kMaxDimC * kMaxDimC]; // constitutive matrix (row-major dimC x dimC): kernel-parameter space = constant bank
-};
 
 // ---- the node-row kernel (default) ----------------------------------------------------------------------
 // A group of G lanes owns one NODE-BLOCK row I of K, i.e. the NDN scalar CSR rows of node I at once.  Compared
@@ -812,7 +554,30 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
   double *stag = nullptr;
   uint8_t *degen = nullptr;
-  int rc = scratch_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * S::REC);
+  int rc;
+  if constexpr (NN <= 4) {
+    const char *rows_env0 = getenv("FEMB200_ROWS");
+    if (rows_env0 && !strcmp(rows_env0, "fused") && sym->rowcols && sh.nqp <= 9) {
+      // fused scalar-row path: checks only (k_geometry without stores), then the kernel that recomputes what it needs
+      double4 *nodes4 = nullptr;
+      if ((rc = scratch_alloc(ctx, &nodes4, (size_t)ga->n_nodes))) return rc;
+      FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
+      if (n_elem) {
+        k_geometry<D, NN, BKIND, TAB_CONST, false><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, ga->d_nodes, conn32, nullptr, nullptr, ctx->d_err, d_tab,
+                                                                                                 tl.offW, tl.offN, tl.offDN, sh.nqp);
+        ctx->launches++;
+      }
+      FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
+      RowArgs a;
+      a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
+      a.stag = nullptr; a.degen = nullptr; a.order = nullptr; a.v0 = 0; a.v1 = ga->n_nodes; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
+      for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
+      rc = srows_fused(ctx, sh, a, ga->d_nodes, sym->rowcols, sym->cols_stride, h_tab, nullptr, 0, ga->n_nodes, sym->max_rowlen, nodes4);
+      FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
+      if (rc != -2) { ga->split_numeric = true; return rc; }
+    }
+  }
+  rc = scratch_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * S::REC);
   if (rc) return rc;
   if ((rc = scratch_alloc(ctx, &degen, (size_t)n_elem))) return rc;
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
@@ -829,6 +594,16 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   rc = -2;
   const int64_t nn_ = a.n_nodes;
   constexpr bool PACKED = NN == 8 || NN == 20;
+  const char *rows_env = getenv("FEMB200_ROWS");
+  if (rows_env && !strcmp(rows_env, "srow")) {
+    if (sym->order && sym->n_short > 0 && sym->n_short < nn_) {
+      rc = srows_staged(ctx, sh, a, sym->order, 0, sym->n_short, sym->max_rowlen / 2);
+      if (rc == 0) rc = srows_staged(ctx, sh, a, sym->order, sym->n_short, nn_, sym->max_rowlen);
+    } else {
+      rc = srows_staged(ctx, sh, a, nullptr, 0, nn_, sym->max_rowlen);
+    }
+  }
+  if (rc == -2)
   if (!PACKED && sym->order && sym->n_short > 0 && sym->n_short < nn_ && gsel == G0) {
     // two launches (see k_class_flags): short rows (rowlen <= max/2) with half the accumulators per row, then the long
     // (and empty) rows.  (More lanes per row for the long class was measured: no difference.)

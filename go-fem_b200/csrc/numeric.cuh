@@ -1,0 +1,280 @@
+// numeric.cuh -- device helpers shared by the numeric kernels (numeric.cu, srows.cu): strain-displacement block
+// structure, table access, Jacobian determinant / inverse, per-quadrature-point geometry, staged record layout.
+#pragma once
+#include "common.cuh"
+#include <type_traits>
+
+namespace femb200 {
+
+static __constant__ double c_tab[kTabDoubles]; // per translation unit; only numeric.cu uploads and reads its copy
+
+// ---- strain-displacement block structure ---------------------------------------------------------
+// Node "values" v[] and the selector sel(k,i): B_node[k][i] = v[sel] (or 0 when sel < 0).
+//  XYZ            v = (gx, gy, gz)              straindisplacement.go:5-26
+//  PLANE          v = (gx, gy)                  straindisplacement.go:28-40
+//  AXISYM         v = (gr, gz, N/r)             straindisplacement.go:42-58
+//  THERMAL        v = (g0..g_{d-1})             thermal.go:18-21,31-34 (B = dN)
+//  THERMAL_AXISYM v = (N/r + gr, gz)            thermal.go:43-56
+template <int BKIND, int D> struct BT;
+template <> struct BT<FEMB200_B_XYZ, 3> {
+  static constexpr int NDN = 3, DIMC = 6, NV = 3; static constexpr bool RADIAL = false;
+  __host__ __device__ static constexpr int sel(int k, int i) {
+    constexpr int t[6][3] = {{0, -1, -1}, {-1, 1, -1}, {-1, -1, 2}, {1, 0, -1}, {-1, 2, 1}, {2, -1, 0}};
+    return t[k][i];
+  }
+};
+template <> struct BT<FEMB200_B_PLANE, 2> {
+  static constexpr int NDN = 2, DIMC = 3, NV = 2; static constexpr bool RADIAL = false;
+  __host__ __device__ static constexpr int sel(int k, int i) {
+    constexpr int t[3][2] = {{0, -1}, {-1, 1}, {1, 0}};
+    return t[k][i];
+  }
+};
+template <> struct BT<FEMB200_B_AXISYM, 2> {
+  static constexpr int NDN = 2, DIMC = 4, NV = 3; static constexpr bool RADIAL = true;
+  __host__ __device__ static constexpr int sel(int k, int i) {
+    constexpr int t[4][2] = {{0, -1}, {2, -1}, {-1, 1}, {1, 0}};
+    return t[k][i];
+  }
+};
+template <int D> struct BT<FEMB200_B_THERMAL, D> {
+  static constexpr int NDN = 1, DIMC = D, NV = D; static constexpr bool RADIAL = false;
+  __host__ __device__ static constexpr int sel(int k, int i) { return k; }
+};
+template <> struct BT<FEMB200_B_THERMAL_AXISYM, 2> {
+  static constexpr int NDN = 1, DIMC = 2, NV = 2; static constexpr bool RADIAL = true;
+  __host__ __device__ static constexpr int sel(int k, int i) { return k; }
+};
+
+// ---- table access: __constant__ (uniform broadcast) or global fallback for oversized tables -------
+template <bool TAB_CONST> struct Tab {
+  const double *g;
+  int offW, offN, offDN;
+  __device__ __forceinline__ double at(int i) const {
+    if constexpr (TAB_CONST) return c_tab[i]; else return __ldg(g + i);
+  }
+  template <int DIMC> __device__ __forceinline__ double C(int k, int c) const { return at(k * DIMC + c); }
+  __device__ __forceinline__ double w(int q) const { return at(offW + q); }
+  template <int NN> __device__ __forceinline__ double N(int q, int b) const { return at(offN + q * NN + b); }
+  template <int D, int NN> __device__ __forceinline__ double dN(int q, int i, int b) const { return at(offDN + (q * D + i) * NN + b); }
+};
+
+// ---- d x d determinant and inverse --------------------------------------------------------------
+// The determinant follows the reference's algorithm class: LU with partial pivoting (gonum mat.Det ->
+// Dgetf2, first-max pivot, multipliers = a * (1/pivot)), det = sign * prod(u_ii), so that exactly singular
+// Jacobians (collapsed elements: two identical rows) give EXACTLY 0 -> "zero determinant", and the
+// sign of a degenerate element is not decided by FMA rounding noise.  The inverse is the adjugate
+// scaled by 1/det (differences to the reference's LU solve are O(eps * cond)).
+template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D][D]) {
+  double A[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) A[i][j] = Jin[i][j];
+  double det = 1.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    // first index of the largest |A[i][j]|, i >= j; swap it into row j (predicated, static indices)
+    double best = fabs(A[j][j]);
+    int p = j;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      const double v = fabs(A[i][j]);
+      if (v > best) { best = v; p = i; }
+    }
+#pragma unroll
+    for (int i = j + 1; i < D; ++i)
+      if (p == i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) { const double t = A[j][k]; A[j][k] = A[i][k]; A[i][k] = t; }
+        det = -det;
+      }
+    const double piv = A[j][j];
+    det = __dmul_rn(det, piv);
+    if (piv != 0.0) {
+      const double r = 1.0 / piv;
+#pragma unroll
+      for (int i = j + 1; i < D; ++i) {
+        const double l = __dmul_rn(A[i][j], r);
+#pragma unroll
+        for (int k = j + 1; k < D; ++k) A[i][k] = __dsub_rn(A[i][k], __dmul_rn(l, A[j][k])); // no FMA: same rounding as the reference's LU
+      }
+    }
+  }
+  return det;
+}
+
+template <int D> __device__ __forceinline__ double inv_det(const double (&J)[D][D], double (&inv)[D][D]);
+template <> __device__ __forceinline__ double inv_det<1>(const double (&J)[1][1], double (&inv)[1][1]) {
+  inv[0][0] = 1.0 / J[0][0];
+  return J[0][0];
+}
+template <> __device__ __forceinline__ double inv_det<2>(const double (&J)[2][2], double (&inv)[2][2]) {
+  const double det = lu_det<2>(J);
+  const double r = 1.0 / det;
+  inv[0][0] = J[1][1] * r; inv[0][1] = -J[0][1] * r;
+  inv[1][0] = -J[1][0] * r; inv[1][1] = J[0][0] * r;
+  return det;
+}
+template <> __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&inv)[3][3]) {
+  const double det = lu_det<3>(J);
+  const double r = 1.0 / det;
+  inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * r;
+  inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * r;
+  inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * r;
+  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+  inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+  inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+  inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+  inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+  return det;
+}
+template <int D> __device__ __forceinline__ double norm1(const double (&A)[D][D]) {
+  double m = 0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += fabs(A[i][j]);
+    m = fmax(m, s);
+  }
+  return m;
+}
+
+// Geometry of one quadrature point.  Returns the error kind (0 = ok) exactly where the reference
+// would have returned it (assembler_isoparametric.go:95-107).
+template <int D, int NN, bool RADIAL, class TabT>
+__device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double (&X)[NN][D], double (&inv)[D][D],
+                                           double &detJ, double &rinv, double &scale) {
+  double J[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) J[i][j] = 0.0;
+#pragma unroll
+  for (int b = 0; b < NN; ++b)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double dn = tab.template dN<D, NN>(q, i, b);
+#pragma unroll
+      for (int j = 0; j < D; ++j) J[i][j] = __dadd_rn(J[i][j], __dmul_rn(dn, X[b][j])); // jac.Mul(dN, X): node-ascending, unfused (:93)
+    }
+  detJ = inv_det<D>(J, inv);
+  if (detJ < 0) return FEMB200_ERR_NEG_DET;
+  if (detJ < 1e-12) return FEMB200_ERR_ZERO_DET;
+  if (norm1<D>(J) * norm1<D>(inv) > 1e16) return FEMB200_ERR_SOLVE;
+  scale = 1.0;
+  rinv = 0.0;
+  if constexpr (RADIAL) {
+    double r = 0.0;
+#pragma unroll
+    for (int b = 0; b < NN; ++b) r = fma(X[b][0], tab.template N<NN>(q, b), r);
+    rinv = 1.0 / r;
+    scale = r;
+    if (isnan(r)) return FEMB200_ERR_NAN_SCALE;
+  }
+  return 0;
+}
+
+// v[] of one node at quadrature point q (see BT above)
+template <int BKIND, int D, int NN, class TabT>
+__device__ __forceinline__ void node_vals(const TabT &tab, int q, int b, const double (&inv)[D][D], double rinv,
+                                          double (&v)[BT<BKIND, D>::NV]) {
+  double g[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) s = fma(inv[i][j], tab.template dN<D, NN>(q, j, b), s);
+    g[i] = s;
+  }
+  if constexpr (BKIND == FEMB200_B_AXISYM) {
+    v[0] = g[0]; v[1] = g[1]; v[2] = tab.template N<NN>(q, b) * rinv;
+  } else if constexpr (BKIND == FEMB200_B_THERMAL_AXISYM) {
+    v[0] = tab.template N<NN>(q, b) * rinv + g[0]; v[1] = g[1];
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = g[i];
+  }
+}
+
+// E = f * B_a^T C   (NDN x DIMC), only the structural non-zeros of B_a are touched
+template <int BKIND, int D, class TabT>
+__device__ __forceinline__ void bt_c(const TabT &tab, const double (&va)[BT<BKIND, D>::NV], double f,
+                                     double (&E)[BT<BKIND, D>::NDN][BT<BKIND, D>::DIMC]) {
+  using B = BT<BKIND, D>;
+  double vs[B::NV];
+#pragma unroll
+  for (int i = 0; i < B::NV; ++i) vs[i] = va[i] * f;
+#pragma unroll
+  for (int i = 0; i < B::NDN; ++i)
+#pragma unroll
+    for (int c = 0; c < B::DIMC; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < B::DIMC; ++k)
+        if (B::sel(k, i) >= 0) s = fma(vs[B::sel(k, i)], tab.template C<B::DIMC>(k, c), s);
+      E[i][c] = s;
+    }
+}
+
+// blk = E * B_b  (NDN x NDN)
+template <int BKIND, int D>
+__device__ __forceinline__ void e_b(const double (&E)[BT<BKIND, D>::NDN][BT<BKIND, D>::DIMC],
+                                    const double (&vb)[BT<BKIND, D>::NV],
+                                    double (&blk)[BT<BKIND, D>::NDN * BT<BKIND, D>::NDN]) {
+  using B = BT<BKIND, D>;
+#pragma unroll
+  for (int i = 0; i < B::NDN; ++i)
+#pragma unroll
+    for (int j = 0; j < B::NDN; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < B::DIMC; ++k)
+        if (B::sel(k, j) >= 0) s = fma(E[i][k], vb[B::sel(k, j)], s);
+      blk[i * B::NDN + j] = s;
+    }
+}
+
+
+template <int BKIND, int D, int NN> struct Stag {
+  using B = BT<BKIND, D>;
+  static constexpr bool FIN = (B::NV == 3);                 // f stored in every node's 4th slot
+  static constexpr int NVP = FIN ? 4 : B::NV;               // doubles per node
+  static constexpr int REC = FIN ? NN * 4 : ((NN * B::NV + 2) & ~1);
+  static constexpr int FOFF = NN * B::NV;                   // !FIN: position of f
+};
+
+__device__ __forceinline__ void ld256(const double *p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+struct RowArgs {
+  int64_t n_nodes;
+  int64_t n_numeric;          // elements [n_numeric, n_elem) are pattern-only (halo): no values
+  const int32_t *n2e_ptr;
+  const uint32_t *n2e_t;
+  const uint16_t *pos16;
+  const int64_t *blkptr;
+  const double *stag;
+  const uint8_t *degen;
+  const int32_t *order;       // visiting order of the node rows (NULL: identity)
+  int64_t v0, v1;             // visiting range of this launch
+  double *values;
+  int64_t ninc;               // n_elem * nn (length of n2e_t)
+  int nqp;
+  double C[kMaxDimC * kMaxDimC]; // constitutive matrix (row-major dimC x dimC): kernel-parameter space = constant bank
+};
+
+// srows.cu: the scalar-row kernel (thread per scalar CSR row); -2 = does not apply, keep the node-row kernel
+int srows_staged(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap);
+
+int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *rowcols, int cols_stride,
+                const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4);
+
+} // namespace femb200

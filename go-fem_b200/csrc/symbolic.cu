@@ -498,6 +498,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   // ---- node-block row pattern ----------------------------------------------------------------
   int32_t *tmpcols = nullptr;
   if ((rc = scratch_alloc(ctx, &tmpcols, ninc * nn))) return rc;
+  out->rowcols = tmpcols; out->cols_stride = nn;
   if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn))) return rc;
   FEMB_CUDA_OK(ctx, cudaMemsetAsync(rowlen + n_nodes, 0, sizeof(int64_t), st));
   switch (nn) {
