@@ -115,6 +115,7 @@ static void free_plan(femb200_assembler *ga) {
   dev_free(ctx, ga->plan.n2e_ptr);
   dev_free(ctx, ga->plan.n2e_t);
   dev_free(ctx, ga->plan.pos16);
+  dev_free(ctx, ga->plan.blkcols);
   dev_free(ctx, ga->plan.blkptr);
   dev_free(ctx, ga->plan.conn32);
   dev_free(ctx, ga->plan.order);
@@ -226,7 +227,7 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   ScratchScope scratch_scope(ctx); // staged, d_tab, symbolic / numeric temporaries: released on every return path
   auto cleanup = [&]() { dev_free(ctx, conn32); };
   auto drop_sym = [&]() {
-    dev_free(ctx, sym.n2e_ptr); dev_free(ctx, sym.n2e_t); dev_free(ctx, sym.pos16); dev_free(ctx, sym.blkptr); dev_free(ctx, sym.order);
+    dev_free(ctx, sym.n2e_ptr); dev_free(ctx, sym.n2e_t); dev_free(ctx, sym.pos16); dev_free(ctx, sym.blkptr); dev_free(ctx, sym.order); dev_free(ctx, sym.blkcols);
     dev_free(ctx, sym.csr.indptr); dev_free(ctx, sym.csr.indices); dev_free(ctx, sym.csr.values);
   };
   rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged);
@@ -242,7 +243,7 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   if (rc == -1) rc = decode_error(ga);
   if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; }
 
-  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), conn32, n_elem - n_pattern_only, &sym);
+  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), conn32, n_elem - n_pattern_only, &sym, n_elem);
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);
@@ -256,6 +257,7 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   free_plan(ga);
   ga->plan.nn = sh.nn; ga->plan.nu = sh.nu; ga->plan.n_elem = n_elem;
   ga->plan.n2e_ptr = sym.n2e_ptr; ga->plan.n2e_t = sym.n2e_t; ga->plan.pos16 = sym.pos16; ga->plan.blkptr = sym.blkptr;
+  ga->plan.blkcols = sym.blkcols;
   ga->plan.conn32 = conn32; conn32 = nullptr;
   ga->plan.order = sym.order; ga->plan.n_short = sym.n_short;
   ga->plan.n_numeric = n_elem - n_pattern_only;
@@ -340,14 +342,14 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
   if ((ce = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
   if ((rc = dev_alloc(ctx, &newvals, (size_t)ga->K.nnz))) return fail(rc);
   SymbolicResult sym;
-  sym.n2e_ptr = pl.n2e_ptr; sym.n2e_t = pl.n2e_t; sym.pos16 = pl.pos16; sym.blkptr = pl.blkptr;
+  sym.n2e_ptr = pl.n2e_ptr; sym.n2e_t = pl.n2e_t; sym.pos16 = pl.pos16; sym.blkptr = pl.blkptr; sym.blkcols = pl.blkcols;
   sym.max_rowlen = pl.max_rowlen;
   sym.order = pl.order; sym.n_short = pl.n_short;
   for (int s = 0; s < 4; ++s) sym.group_need[s] = pl.group_need[s];
   sym.csr.n_rows = ga->K.n_rows; sym.csr.nnz = ga->K.nnz; sym.csr.indptr = ga->K.indptr; sym.csr.indices = ga->K.indices;
   sym.csr.values = newvals;
   if ((ce = cudaEventRecord(ctx->ev[4], st)) != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
-  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), pl.conn32, pl.n_numeric, &sym);
+  rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), pl.conn32, pl.n_numeric, &sym, pl.n_elem);
   if (!rc) {
     ce = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev[5], st);

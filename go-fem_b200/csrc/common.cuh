@@ -14,6 +14,12 @@ constexpr int kMaxD = 3;
 constexpr int kMaxNdn = 6;       // DofsFlag has 6 named bits (fem.go:70-82)
 constexpr int kMaxDimC = 6;
 constexpr int kTabDoubles = 5632; // 44 KB of __constant__ table space (N | dN | w | C)
+// Slot map entries pos16[k][b] (row-local block position of node b of the element of incidence k).  For elements with
+// <= 4 nodes the two top bits of entry b = 0 also carry the local index of the row's own node in the element, so the
+// fused scalar-row kernel reads ONE 8-byte word per incident element and never touches the incidence list.
+constexpr int kPosLaShift = 14;
+constexpr unsigned kPosMask = 0x3fffu;
+__host__ __device__ inline unsigned pos_mask(int nn) { return nn <= 4 ? kPosMask : 0xffffu; }
 
 // Layout of the per-call table blob (doubles): [C dimC*dimC][w nqp][N nqp*nn][dN nqp*d*nn]
 struct TabLayout {
@@ -57,6 +63,7 @@ struct LastPlan {
   int32_t *order = nullptr;     // two-class visiting order (see SymbolicResult), or NULL
   int64_t n_short = 0;
   int64_t n_numeric = 0;        // elements [n_numeric, n_elem) are pattern-only
+  int32_t *blkcols = nullptr;   // [nblk] column node of every node block (row I: blkcols[blkptr[I] ...], ascending)
   int64_t nblk = 0;             // node blocks of this call's pattern: K.nnz must equal nu*nu*nblk while matches_K holds
   int d = 0, ndn = 0, bkind = 0, max_rowlen = 0;
   int64_t group_need[4] = {0, 0, 0, 0};
@@ -183,8 +190,7 @@ struct SymbolicResult {
   int32_t *order = nullptr;   // two-class visiting order of the node rows (short rows first), or NULL
   int64_t n_short = 0;        // rows [0, n_short) of `order` have rowlen <= max_rowlen / 2
   int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive rows of sum(rowlen)
-  const int32_t *rowcols = nullptr; // ascending column nodes of row I at rowcols[cols_stride * n2e_ptr[I] ...] (call scratch)
-  int cols_stride = 0;
+  int32_t *blkcols = nullptr;       // [nblk] column node of every node block
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)
 };
 
@@ -192,7 +198,7 @@ struct SymbolicResult {
 int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *conn32, int64_t n_elem,
                    SymbolicResult *out);
 int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, int tab_doubles,
-                  const int32_t *conn32, int64_t n_elem, SymbolicResult *sym);
+                  const int32_t *conn32, int64_t n_elem, SymbolicResult *sym, int64_t n_elem_total);
 bool numeric_supported(const ElemShape &sh);
 int csr_merge_into(femb200_assembler *ga, DeviceCsr *add); // K += add (consumes add)
 int csr_accumulate_rows(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,

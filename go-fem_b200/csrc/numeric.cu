@@ -34,6 +34,7 @@ struct NumArgs {
   const double *h_tab;        // host copy of the table blob (C first)
   int offW, offN, offDN, nqp;
   int nu;                     // distinct dofmap values (== NDN when identity)
+  int64_t n_elem_total;       // numeric + pattern-only elements of the call
   int dof2u[kMaxNdn];
 };
 
@@ -119,14 +120,14 @@ k_numeric_rows(const NumArgs a) {
 #pragma unroll
           for (int m = 0; m < NB2; ++m) acc[b][m] += blk[m];
         } else {
-          add_block(pk[b], blk);
+          add_block(pk[b] & pos_mask(NN), blk);
         }
       }
     }
     if constexpr (ACC_REGS) {
       if (!bad) {
 #pragma unroll
-        for (int b = 0; b < NN; ++b) add_block(pk[b], acc[b]);
+        for (int b = 0; b < NN; ++b) add_block(pk[b] & pos_mask(NN), acc[b]);
       }
     }
   }
@@ -337,11 +338,11 @@ k_noderows(const RowArgs a) {
 #pragma unroll
       for (int v4 = 0; v4 < NN / 4; ++v4) {
         const uint2 w = __ldg(reinterpret_cast<const uint2 *>(pk) + v4);
-        pos[4 * v4] = w.x & 0xffff; pos[4 * v4 + 1] = w.x >> 16; pos[4 * v4 + 2] = w.y & 0xffff; pos[4 * v4 + 3] = w.y >> 16;
+        pos[4 * v4] = w.x & pos_mask(NN); pos[4 * v4 + 1] = w.x >> 16; pos[4 * v4 + 2] = w.y & 0xffff; pos[4 * v4 + 3] = w.y >> 16;
       }
     } else {
 #pragma unroll
-      for (int s = 0; s < NB; ++s) pos[s] = (g + G * s < NN) ? (int)__ldg(pk + g + G * s) : 0;
+      for (int s = 0; s < NB; ++s) pos[s] = (g + G * s < NN) ? (int)(__ldg(pk + g + G * s) & pos_mask(NN)) : 0;
     }
   };
 
@@ -537,7 +538,7 @@ static int launch_noderows(femb200_ctx *ctx, const RowArgs &a0, const SymbolicRe
 
 template <int D, int NN, int BKIND, bool TAB_CONST>
 static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, const int32_t *conn32,
-                        int64_t n_elem, SymbolicResult *sym) {
+                        int64_t n_elem, SymbolicResult *sym, int64_t n_elem_total) {
   femb200_ctx *ctx = ga->ctx;
   using B = BT<BKIND, D>;
   using S = Stag<BKIND, D, NN>;
@@ -556,9 +557,11 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   uint8_t *degen = nullptr;
   int rc;
   if constexpr (NN <= 4) {
+    // default for elements with <= 4 nodes: the fused scalar-row kernel (srows.cu).  k_geometry runs without stores, as
+    // the reference's per-element checks only; FEMB200_ROWS=noderows keeps the staged node-row kernel.
     const char *rows_env0 = getenv("FEMB200_ROWS");
-    if (rows_env0 && !strcmp(rows_env0, "fused") && sym->rowcols && sh.nqp <= 9) {
-      // fused scalar-row path: checks only (k_geometry without stores), then the kernel that recomputes what it needs
+    const bool want_fused = !(rows_env0 && (!strcmp(rows_env0, "noderows") || !strcmp(rows_env0, "srow")));
+    if (want_fused && sym->blkcols && sh.nqp <= 9) {
       double4 *nodes4 = nullptr;
       if ((rc = scratch_alloc(ctx, &nodes4, (size_t)ga->n_nodes))) return rc;
       FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
@@ -571,8 +574,9 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
       RowArgs a;
       a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
       a.stag = nullptr; a.degen = nullptr; a.order = nullptr; a.v0 = 0; a.v1 = ga->n_nodes; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
+      a.has_halo = n_elem < n_elem_total ? 1 : 0;
       for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
-      rc = srows_fused(ctx, sh, a, ga->d_nodes, sym->rowcols, sym->cols_stride, h_tab, nullptr, 0, ga->n_nodes, sym->max_rowlen, nodes4);
+      rc = srows_fused(ctx, sh, a, ga->d_nodes, sym->blkcols, h_tab, nullptr, 0, ga->n_nodes, sym->max_rowlen, nodes4);
       FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
       if (rc != -2) { ga->split_numeric = true; return rc; }
     }
@@ -590,6 +594,7 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   RowArgs a;
   a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
   a.stag = stag; a.degen = degen; a.order = nullptr; a.v0 = 0; a.v1 = ga->n_nodes; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
+  a.has_halo = n_elem < n_elem_total ? 1 : 0;
   for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
   rc = -2;
   const int64_t nn_ = a.n_nodes;
@@ -659,8 +664,8 @@ static int launch_rows(femb200_assembler *ga, const ElemShape &sh, NumArgs &a, b
   const bool force_global = getenv("FEMB200_FORCE_GLOBAL_ACC") != nullptr;
   const bool force_thread_rows = getenv("FEMB200_FORCE_THREAD_ROWS") != nullptr;
   if (sh.identity && !force_global && !force_thread_rows) {
-    rc = tab_const ? launch_dof_T<D, NN, BKIND, true>(ga, sh, a.tab_g, a.h_tab, a.conn, n_elem, sym)
-                   : launch_dof_T<D, NN, BKIND, false>(ga, sh, a.tab_g, a.h_tab, a.conn, n_elem, sym);
+    rc = tab_const ? launch_dof_T<D, NN, BKIND, true>(ga, sh, a.tab_g, a.h_tab, a.conn, n_elem, sym, a.n_elem_total)
+                   : launch_dof_T<D, NN, BKIND, false>(ga, sh, a.tab_g, a.h_tab, a.conn, n_elem, sym, a.n_elem_total);
     if (rc != -2) return rc;
   }
   if (sh.identity && !force_global)
@@ -707,7 +712,7 @@ bool numeric_supported(const ElemShape &sh) {
 }
 
 int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, int tab_doubles,
-                  const int32_t *conn32, int64_t n_elem, SymbolicResult *sym) {
+                  const int32_t *conn32, int64_t n_elem, SymbolicResult *sym, int64_t n_elem_total) {
   femb200_ctx *ctx = ga->ctx;
   if (!numeric_supported(sh)) return FEMB200_ERR_UNSUPPORTED;
   const bool tab_const = tab_doubles <= kTabDoubles && !ctx->concurrent; // __constant__ tables are per device: one call at a time
@@ -729,6 +734,7 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
   a.h_tab = h_tab;
   a.offW = tl.offW; a.offN = tl.offN; a.offDN = tl.offDN; a.nqp = sh.nqp;
   a.nu = sh.nu;
+  a.n_elem_total = n_elem_total;
   for (int i = 0; i < kMaxNdn; ++i) a.dof2u[i] = sh.dof2u[i];
   switch (sh.bkind) {
   case FEMB200_B_XYZ: return dispatch_nn<3, FEMB200_B_XYZ>(ga, sh, a, tab_const, sym, n_elem);

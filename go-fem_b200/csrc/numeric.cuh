@@ -268,13 +268,14 @@ struct RowArgs {
   double *values;
   int64_t ninc;               // n_elem * nn (length of n2e_t)
   int nqp;
+  int has_halo;               // some incidences belong to pattern-only elements (>= n_numeric): the incidence list must be consulted
   double C[kMaxDimC * kMaxDimC]; // constitutive matrix (row-major dimC x dimC): kernel-parameter space = constant bank
 };
 
 // srows.cu: the scalar-row kernel (thread per scalar CSR row); -2 = does not apply, keep the node-row kernel
 int srows_staged(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap);
 
-int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *rowcols, int cols_stride,
+int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *blkcols,
                 const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4);
 
 } // namespace femb200

@@ -136,6 +136,30 @@ __device__ __forceinline__ void srow_copy_out_inplace(double *acc_w, bool act, i
   }
 }
 
+// Long rows (more than 48 entries per scalar row): 16 entries of every scalar row at a time through a small staging buffer
+// (32 x 17 doubles, the dead coordinate cache): own accumulators -> staging (odd stride: conflict free) -> 128-byte
+// segments of the final rows, two scalar rows per iteration.
+__device__ __forceinline__ void srow_copy_out_chunked(const double *acc_w, double *stage, int lane, int rowsz, double *vrow_mine) {
+  int mx = rowsz;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const int half = lane >> 4, l16 = lane & 15;
+  for (int c0 = 0; c0 < mx; c0 += 16) {
+#pragma unroll
+    for (int mm = 0; mm < 16; ++mm)
+      if (c0 + mm < rowsz) stage[lane * 17 + mm] = acc_w[(c0 + mm) * 32 + lane];
+    __syncwarp();
+#pragma unroll 1
+    for (int o = 0; o < 32; o += 2) {
+      const int src_lane = o + half;
+      const int n = __shfl_sync(0xffffffffu, rowsz, src_lane);
+      const unsigned long long vp = __shfl_sync(0xffffffffu, (unsigned long long)vrow_mine, src_lane);
+      if (c0 + l16 < n) reinterpret_cast<double *>(vp)[c0 + l16] = stage[src_lane * 17 + l16];
+    }
+    __syncwarp();
+  }
+}
+
 struct SRowExtra {
   int cap_m;        // accumulator entries per thread (rl_cap * NDN)
   int stage_cap;    // doubles of copy-out staging per warp
@@ -195,13 +219,13 @@ k_srows(const RowArgs a, const SRowExtra x) {
       const uint2 w = __ldg(reinterpret_cast<const uint2 *>(a.pos16 + (int64_t)k * NN));
       const unsigned long long w64 = ((unsigned long long)w.y << 32) | w.x;
 #pragma unroll
-      for (int bp = 0; bp < NN; ++bp) pr[bp] = (int)((w64 >> (16 * ((la + bp) & 3))) & 0xffffu);
+      for (int bp = 0; bp < NN; ++bp) pr[bp] = (int)((w64 >> (16 * ((la + bp) & 3))) & kPosMask);
     } else {
 #pragma unroll
       for (int bp = 0; bp < NN; ++bp) {
         int b = la + bp;
         if (b >= NN) b -= NN;
-        pr[bp] = (int)__ldg(a.pos16 + (int64_t)k * NN + b);
+        pr[bp] = (int)(__ldg(a.pos16 + (int64_t)k * NN + b) & pos_mask(NN));
       }
     }
     double blk[NN][NDN];
@@ -336,8 +360,7 @@ struct FusedTab {                       // [q][..] tables of the call (assembler
 };
 struct FusedIn {
   const double4 *nodes4;                // [n_nodes] (x, y, z, 0)
-  const int32_t *rowcols;               // ascending column nodes of row I at rowcols[cols_stride * n2e_ptr[I] ...]
-  int cols_stride;
+  const int32_t *blkcols;               // ascending column nodes of row I at blkcols[blkptr[I] ...]
   int rl_cap;
 };
 
@@ -410,7 +433,7 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
 #pragma unroll
   for (int j = 0; j < D; ++j) X0[j] = 0.0;
   if (rl) {
-    const int32_t *cols = fi.rowcols + (int64_t)fi.cols_stride * beg;
+    const int32_t *cols = fi.blkcols + b0;
     for (int p = i; p < rl; p += NDN) {
       double c4[4];
       ld256(reinterpret_cast<const double *>(fi.nodes4 + __ldg(cols + p)), c4);
@@ -445,16 +468,16 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
       for (int b = 0; b < NN; ++b) w64 |= (unsigned long long)__ldg(a.pos16 + (int64_t)k * NN + b) << (16 * b);
     }
   };
-  uint32_t tn = 0u;
+  // pattern-only (halo) elements sit at the end of every incidence list: find the end of the numeric part once
+  if (a.has_halo) {
+    while (end > beg && (int64_t)(__ldg(a.n2e_t + end - 1) / NN) >= a.n_numeric) --end;
+  }
   unsigned long long wn = 0ull;
-  if (beg < end) { tn = __ldg(a.n2e_t + beg); load_pos(beg, wn); }
+  if (beg < end) load_pos(beg, wn);
   for (int k = beg; k < end; ++k) {
-    const uint32_t t = tn;
     const unsigned long long w64 = wn;
-    const int64_t e = t / NN;
-    if (e >= a.n_numeric) break;
-    const int la = (int)(t - (uint32_t)e * NN);
-    if (k + 1 < end) { tn = __ldg(a.n2e_t + k + 1); load_pos(k + 1, wn); }
+    const int la = (int)((w64 >> kPosLaShift) & 3u);
+    if (k + 1 < end) load_pos(k + 1, wn);
     if constexpr (SIMPLEX) {
       // rotated order: node b' of this visit = element node (la + b') mod NN; b' = 0 is node I itself
       int pr[NN];
@@ -462,7 +485,7 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
       for (int bp = 0; bp < NN; ++bp) {
         int b = la + bp;
         if (b >= NN) b -= NN;
-        pr[bp] = (int)((w64 >> (16 * b)) & 0xffffu);
+        pr[bp] = (int)((w64 >> (16 * b)) & kPosMask);
       }
       double ed[D][D];                                           // edge vectors e_k = X[k] - X[0], k = 1..D
 #pragma unroll
@@ -535,7 +558,7 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
     } else {
       int pos[NN];
 #pragma unroll
-      for (int b = 0; b < NN; ++b) pos[b] = (int)((w64 >> (16 * b)) & 0xffffu);
+      for (int b = 0; b < NN; ++b) pos[b] = (int)((w64 >> (16 * b)) & kPosMask);
       double X[NN][D];
 #pragma unroll
       for (int b = 0; b < NN; ++b) {
@@ -631,7 +654,8 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
   __syncwarp();
   double *const vrow_mine = a.values + (int64_t)NDN * NDN * b0 + (int64_t)i * rowsz;
   if (x.cap_m <= 24) srow_copy_out_inplace<NDN, 24>(acc_w, act, lane, i, rowsz, vrow_mine);
-  else srow_copy_out_inplace<NDN, 48>(acc_w, act, lane, i, rowsz, vrow_mine);
+  else if (x.cap_m <= 48) srow_copy_out_inplace<NDN, 48>(acc_w, act, lane, i, rowsz, vrow_mine);
+  else srow_copy_out_chunked(acc_w, s_stage, lane, rowsz, vrow_mine);
 }
 
 __global__ void k_pad_nodes(int64_t n, const double *__restrict__ nodes, double4 *__restrict__ out) {
@@ -649,9 +673,10 @@ static int launch_fused_T(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &
   x.cap_m = (int)rowlen_cap * B::NDN;
   const int node_tot = (int)rowlen_cap * B::NDN * B::NDN;
   (void)node_tot;
-  if (x.cap_m > 48) return -2;                                   // register transposition of the copy-out: scalar rows of <= 48 entries
-  const int cache = NPW * (int)rowlen_cap * D;                   // coordinate cache (doubles) behind the warp's accumulators
-  x.stage_cap = ((cache < 32 ? 32 : cache) + 1) & ~1;          // >= 32: the copy-out pads every scalar row to an odd length
+  int cache = NPW * (int)rowlen_cap * D;                         // coordinate cache (doubles) behind the warp's accumulators
+  if (cache < 32) cache = 32;                                    // the in-place copy-out pads every scalar row to an odd length
+  if (x.cap_m > 48 && cache < 32 * 17) cache = 32 * 17;          // long rows: chunked copy-out staging
+  x.stage_cap = (cache + 1) & ~1;
   const size_t smem = (size_t)NWARP * ((size_t)x.cap_m * 32 + x.stage_cap) * sizeof(double);
   if (smem > ctx->smem_optin) return -2;
   FusedTab tb;
@@ -692,14 +717,14 @@ static int launch_fused_T(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &
 }
 
 // fused front end for elements with <= 4 nodes; returns -2 when it does not apply
-int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *rowcols, int cols_stride,
+int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *blkcols,
                 const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4) {
   if (sh.nn > 4) return -2;
   k_pad_nodes<<<grid_for(a.n_nodes, 256), 256, 0, ctx->stream>>>(a.n_nodes, d_nodes, nodes4);
   ctx->launches++;
   FusedIn fi;
-  fi.nodes4 = nodes4; fi.rowcols = rowcols; fi.cols_stride = cols_stride; fi.rl_cap = 0;
-  const bool t64 = getenv("FEMB200_SROW_TPB") && atoi(getenv("FEMB200_SROW_TPB")) == 64;
+  fi.nodes4 = nodes4; fi.blkcols = blkcols; fi.rl_cap = 0;
+  const bool t64 = !(getenv("FEMB200_SROW_TPB") && atoi(getenv("FEMB200_SROW_TPB")) == 128); // 64-thread blocks: finer shared-memory granularity
 #define FEMB_F(Dv, NNv, BK) return t64 ? launch_fused_T<Dv, NNv, BK, 64>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap) : launch_fused_T<Dv, NNv, BK, 128>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap)
   switch (sh.bkind) {
   case FEMB200_B_XYZ: if (sh.nn == 4) FEMB_F(3, 4, FEMB200_B_XYZ); break;

@@ -148,7 +148,7 @@ k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__
         int mid = (lo + hi) >> 1;
         if (LST(mid) < J) lo = mid + 1; else hi = mid;
       }
-      pos16[(int64_t)k * NN + b] = (uint16_t)lo;
+      pos16[(int64_t)k * NN + b] = (uint16_t)(lo | ((NN <= 4 && b == 0) ? (int)((n2e_t[k] % NN) << kPosLaShift) : 0));
     }
   }
 #undef LST
@@ -297,6 +297,7 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
         while (keys[h] != J) h = (h + 1) & (HS - 1);
         pb[b] = rk[h];
       }
+      if constexpr (NN <= 4) pb[0] |= (int)((tv[s] % NN) << kPosLaShift);
       uint16_t *pk = pos16 + (int64_t)(beg + idx) * NN;
       if constexpr (NN % 4 == 0) {
 #pragma unroll
@@ -378,7 +379,7 @@ template <int NU, int LPN>
 __global__ void __launch_bounds__(256)
 k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ umap_packed, const int32_t *__restrict__ n2e_ptr,
          const int64_t *__restrict__ blkptr, const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices,
-         const int32_t *__restrict__ col_map) {
+         const int32_t *__restrict__ col_map, int32_t *__restrict__ blkcols) {
   const int nu = NU > 0 ? NU : nu_rt;
   const int lane = threadIdx.x & (LPN - 1);
   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPN;
@@ -398,6 +399,7 @@ k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ u
 #pragma unroll
     for (int u = 1; u < (NU > 0 ? NU : kMaxNdn); ++u) off = (uc == u) ? um[u] : off;
     const int32_t J = cols[p];
+    if (uc == 0) blkcols[b0 + p] = J;
     const int32_t c = (col_map ? col_map[J] : J) * mdpn + off;
     for (int ur = 0; ur < nu; ++ur) out[(int64_t)ur * rowsz + idx] = c;
   }
@@ -498,7 +500,6 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   // ---- node-block row pattern ----------------------------------------------------------------
   int32_t *tmpcols = nullptr;
   if ((rc = scratch_alloc(ctx, &tmpcols, ninc * nn))) return rc;
-  out->rowcols = tmpcols; out->cols_stride = nn;
   if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn))) return rc;
   FEMB_CUDA_OK(ctx, cudaMemsetAsync(rowlen + n_nodes, 0, sizeof(int64_t), st));
   switch (nn) {
@@ -547,7 +548,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   for (int s = 0; s < 4; ++s) out->group_need[s] = n_nodes ? ctx->h_scalars[2 + s] : 0;
   if (out->order) out->n_short = ctx->h_scalars[6];
   if (*ctx->h_err != kNoError) return -1; // caller decodes the error word
-  if (out->max_rowlen > 65535) return FEMB200_ERR_TOO_LARGE;
+  if (out->max_rowlen > (int)pos_mask(nn)) return FEMB200_ERR_TOO_LARGE;
 
   // ---- scalar CSR pattern ----------------------------------------------------------------------
   const int nu = sh.nu;
@@ -559,6 +560,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   if ((rc = dev_alloc(ctx, &out->csr.indptr, ndof + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->csr.indices, nnz))) return rc;
   if ((rc = dev_alloc(ctx, &out->csr.values, nnz))) return rc;
+  if ((rc = dev_alloc(ctx, &out->blkcols, (size_t)out->nblk))) return rc;
   unsigned umask = 0;
   for (int i = 0; i < nu; ++i) umask |= 1u << sh.umap[i];
   int *d_umap = nullptr;
@@ -571,8 +573,8 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
     const unsigned eg = grid_for(n_nodes * (small ? 8 : 32), 256);
 #define FEMB_EXPAND(NUV)                                                                                                          \
   do {                                                                                                                          \
-    if (small) k_expand<NUV, 8><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map); \
-    else k_expand<NUV, 32><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map);   \
+    if (small) k_expand<NUV, 8><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map, out->blkcols); \
+    else k_expand<NUV, 32><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map, out->blkcols);   \
   } while (0)
     switch (nu) {
     case 1: FEMB_EXPAND(1); break;
@@ -597,7 +599,7 @@ __global__ void k_slot_map(int64_t ninc, int nn, const int32_t *__restrict__ n2e
   if (k >= ninc) return;
   const uint32_t t = n2e_t[k]; // = e*nn + a
   const int64_t base = blkptr[node_of_k[k]];
-  for (int b = 0; b < nn; ++b) slot[(int64_t)t * nn + b] = base + pos16[k * nn + b];
+  for (int b = 0; b < nn; ++b) slot[(int64_t)t * nn + b] = base + (pos16[k * nn + b] & pos_mask(nn));
 }
 
 __global__ void k_node_of_k(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, int32_t *__restrict__ node_of_k) {
