@@ -35,6 +35,9 @@ int femb200_ctx_create(int device, femb200_ctx **out) {
   CK(cudaMallocHost((void **)&ctx->h_scalars, 8 * sizeof(int64_t)));
   CK(cudaMallocHost((void **)&ctx->h_err, sizeof(unsigned long long)));
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
+  CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
 #undef CK
   *out = ctx;
   return 0;
@@ -52,6 +55,9 @@ void femb200_ctx_destroy(femb200_ctx *ctx) {
   cudaFreeHost(ctx->h_scalars);
   cudaFreeHost(ctx->h_err);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -172,6 +178,7 @@ static int decode_error(femb200_assembler *ga) {
   unsigned long long w = *ga->ctx->h_err;
   if (w == kNoError) return 0;
   ga->err_kind = (int)(w & 0xf);
+  if (ga->err_kind == 0) ga->err_kind = FEMB200_ERR_NODE_OOB; // device encoding, see k_narrow_validate
   ga->err_qp = (int)((w >> 4) & 0xfff);
   ga->err_elem = (int64_t)(w >> 16);
   if (ga->err_kind == FEMB200_ERR_NODE_OOB) ga->err_qp = -1;
@@ -202,9 +209,10 @@ int femb200_add_isoparametric(femb200_assembler *ga, const femb200_elem_desc *de
   return femb200_add_isoparametric_halo(ga, desc, conn, conn_is_int64, conn_on_device, n_elem, 0);
 }
 
-int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn,
-                                   int32_t conn_is_int64, int32_t conn_on_device, int64_t n_elem, int64_t n_pattern_only) {
-  if (!ga || n_elem < 0 || n_pattern_only < 0 || n_pattern_only > n_elem || (n_elem > 0 && !conn)) return FEMB200_ERR_BAD_ARG;
+// One add call.  Host synchronisations: ONE (at the end) when the context holds a size hint for this mesh signature and the
+// fused numeric path applies; otherwise one more between the symbolic and the numeric phase (allocation sizes).
+static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn, int32_t conn_is_int64,
+                                  int32_t conn_on_device, int64_t n_elem, int64_t n_pattern_only, bool allow_hint) {
   femb200_ctx *ctx = ga->ctx;
   cudaStream_t st = ctx->stream;
   FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -215,7 +223,14 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   if (rc) { ga->err_kind = rc; return rc; }
   for (float &f : ga->phase_ms) f = 0.f;
   ga->split_numeric = false;
+  ga->check_done = false;
   const int64_t launches0 = ctx->launches;
+
+  const char *rows_env = getenv("FEMB200_ROWS");
+  const bool fused_ok = sh.identity && sh.nn <= 4 && sh.nqp <= 9 && !(rows_env && (!strcmp(rows_env, "noderows") || !strcmp(rows_env, "srow")));
+  const femb200_ctx::SizeHint &h = ctx->hint;
+  const bool use_hint = allow_hint && fused_ok && h.valid && h.n_nodes == ga->n_nodes && h.n_elem == n_elem && h.nn == sh.nn &&
+                        h.mdpn == ga->mdpn && h.nu == sh.nu && !getenv("FEMB200_NO_HINT");
 
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
   *ctx->h_err = kNoError;
@@ -230,6 +245,13 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
     dev_free(ctx, sym.n2e_ptr); dev_free(ctx, sym.n2e_t); dev_free(ctx, sym.pos16); dev_free(ctx, sym.blkptr); dev_free(ctx, sym.order); dev_free(ctx, sym.blkcols);
     dev_free(ctx, sym.csr.indptr); dev_free(ctx, sym.csr.indices); dev_free(ctx, sym.csr.values);
   };
+  auto fail = [&](int code) {
+    cleanup(); drop_sym();
+    ga->err_kind = code;
+    cudaStreamSynchronize(st);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    return code;
+  };
   rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged);
   if (!rc) rc = scratch_alloc(ctx, &d_tab, blob.size());
   if (!rc) {
@@ -237,21 +259,80 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
   }
   if (!rc && cudaEventRecord(ctx->ev[1], st) != cudaSuccess) { ctx->last_cuda_error = "cudaEventRecord"; rc = FEMB200_ERR_CUDA; }
-  if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; return rc; }
+  if (rc) return fail(rc);
 
-  rc = symbolic_phase(ga, sh, conn32, n_elem, &sym); // synchronises once (nblk, max row length, error word)
-  if (rc == -1) rc = decode_error(ga);
-  if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; }
+  // the reference's per-element checks (:95-107) do not depend on the pattern: on the fused path they run on the second
+  // stream, beside the symbolic phase (FP64 work beside atomics / integer work)
+  bool forked = false;
+  if (fused_ok && ctx->stream2 && n_elem - n_pattern_only > 0 && !getenv("FEMB200_NO_FORK")) {
+    cudaError_t e = cudaEventRecord(ctx->ev_fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); return fail(FEMB200_ERR_CUDA); }
+    rc = check_phase(ga, sh, d_tab, conn32, n_elem - n_pattern_only, ctx->stream2);
+    if (rc == 0) {
+      e = cudaEventRecord(ctx->ev_join, ctx->stream2);
+      if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); return fail(FEMB200_ERR_CUDA); }
+      forked = true;
+      ga->check_done = true;
+    } else if (rc != FEMB200_ERR_UNSUPPORTED) {
+      return fail(rc);
+    }
+    rc = 0;
+  }
+
+  rc = symbolic_phase(ga, sh, conn32, n_elem, &sym, use_hint); // synchronises once unless sized from the hint
+  if (rc == -1) {
+    // a node index is out of range.  The reference's loop is sequential (fem.go:140): an element BEFORE the offending one
+    // may fail its Jacobian checks first, so those checks run over the elements in front of it and the lowest word wins.
+    rc = decode_error(ga);
+    if (rc == FEMB200_ERR_NODE_OOB && !forked && ga->err_elem > 0) {
+      int rc2 = check_phase(ga, sh, d_tab, conn32, ga->err_elem < n_elem - n_pattern_only ? ga->err_elem : n_elem - n_pattern_only, st);
+      if (rc2 == 0) {
+        cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) rc = decode_error(ga);
+      }
+    } else if (forked) {
+      cudaError_t e = cudaStreamSynchronize(ctx->stream2); // the forked checks cover every element already
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) rc = decode_error(ga);
+    }
+  }
+  if (rc) return fail(rc);
 
   rc = numeric_phase(ga, sh, d_tab, blob.data(), (int)blob.size(), conn32, n_elem - n_pattern_only, &sym, n_elem);
+  if (rc == -3) { // hinted sizes unusable on the path this call takes: again, the slow way
+    fail(0);
+    return add_isoparametric_impl(ga, desc, conn, conn_is_int64, conn_on_device, n_elem, n_pattern_only, false);
+  }
   if (!rc) {
-    cudaError_t e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    if (forked) e = cudaStreamWaitEvent(st, ctx->ev_join, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st); // blob / caller buffers are released after this point
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
   }
   if (!rc) rc = decode_error(ga);
-  if (rc) { cleanup(); drop_sym(); ga->err_kind = rc; cudaStreamSynchronize(st); return rc; } // K untouched (:118-120)
+  if (rc) return fail(rc); // K untouched (:118-120)
+  if (sym.speculative) {
+    const int64_t real_maxrl = ctx->h_scalars[0], real_nblk = ctx->h_scalars[1];
+    if (ctx->h_scalars[7] != 0 || real_maxrl > sym.max_rowlen || real_nblk > sym.cap_blk || real_maxrl > (int64_t)pos_mask(sh.nn)) {
+      ctx->hint.valid = false; // a guard tripped: the mesh is not the one the hint came from
+      fail(0);
+      return add_isoparametric_impl(ga, desc, conn, conn_is_int64, conn_on_device, n_elem, n_pattern_only, false);
+    }
+    sym.max_rowlen = (int)real_maxrl;
+    sym.nblk = real_nblk;
+    sym.csr.nnz = (int64_t)sh.nu * sh.nu * real_nblk;
+  }
+  {
+    ctx->hint.valid = true;
+    ctx->hint.n_nodes = ga->n_nodes; ctx->hint.n_elem = n_elem; ctx->hint.nn = sh.nn; ctx->hint.mdpn = ga->mdpn; ctx->hint.nu = sh.nu;
+    ctx->hint.nblk = sym.nblk; ctx->hint.max_rowlen = sym.max_rowlen;
+  }
 
   // commit: K += this call (assembler_isoparametric.go:121); keep the plan for the slot-map query
   free_plan(ga);
@@ -264,23 +345,33 @@ int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_des
   ga->plan.nblk = sym.nblk;
   ga->plan.d = sh.d; ga->plan.ndn = sh.ndn; ga->plan.bkind = sh.bkind; ga->plan.max_rowlen = sym.max_rowlen; ga->plan.identity = sh.identity;
   for (int s = 0; s < 4; ++s) ga->plan.group_need[s] = sym.group_need[s];
-  ga->plan.matches_K = (ga->K.nnz == 0);
-  rc = csr_merge_into(ga, &sym.csr);
+  const bool first = (ga->K.nnz == 0);
+  ga->plan.matches_K = first;
+  rc = csr_merge_into(ga, &sym.csr); // first call on the assembler: adopts the arrays, no device work
   cleanup();
-  FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[6], st));
-  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (!first) { // a union with earlier calls ran on the device: its time belongs to the call
+    FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[6], st));
+    FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  }
   if (rc) { ga->err_kind = rc; return rc; }
   float ms = 0;
-  const int pairs[6][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {4, 5}, {5, 6}};
-  for (int i = 0; i < 6; ++i)
+  const int pairs[5][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {4, 5}};
+  for (int i = 0; i < 5; ++i)
     if (cudaEventElapsedTime(&ms, ctx->ev[pairs[i][0]], ctx->ev[pairs[i][1]]) == cudaSuccess) ga->phase_ms[i] = ms;
-  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]) == cudaSuccess) ga->phase_ms[6] = ms;
+  if (!first && cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ga->phase_ms[5] = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[first ? 5 : 6]) == cudaSuccess) ga->phase_ms[6] = ms;
   ga->phase_ms[7] = (float)(ctx->launches - launches0);
   if (ga->split_numeric) {
     if (cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]) == cudaSuccess) ga->phase_ms[8] = ms;
     if (cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ga->phase_ms[9] = ms;
   }
   return 0;
+}
+
+int femb200_add_isoparametric_halo(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn,
+                                   int32_t conn_is_int64, int32_t conn_on_device, int64_t n_elem, int64_t n_pattern_only) {
+  if (!ga || n_elem < 0 || n_pattern_only < 0 || n_pattern_only > n_elem || (n_elem > 0 && !conn)) return FEMB200_ERR_BAD_ARG;
+  return add_isoparametric_impl(ga, desc, conn, conn_is_int64, conn_on_device, n_elem, n_pattern_only, true);
 }
 
 int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, const double *nodes, int32_t nodes_on_device) {
@@ -299,6 +390,7 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
   if (rc) { ga->err_kind = rc; return rc; }
   for (float &f : ga->phase_ms) f = 0.f;
   ga->split_numeric = false;
+  ga->check_done = false;
   const int64_t launches0 = ctx->launches;
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
   // new coordinates (same node count): nonlinear / moving-mesh re-assembly.  They replace the old ones only if the call
@@ -343,7 +435,7 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
   if ((rc = dev_alloc(ctx, &newvals, (size_t)ga->K.nnz))) return fail(rc);
   SymbolicResult sym;
   sym.n2e_ptr = pl.n2e_ptr; sym.n2e_t = pl.n2e_t; sym.pos16 = pl.pos16; sym.blkptr = pl.blkptr; sym.blkcols = pl.blkcols;
-  sym.max_rowlen = pl.max_rowlen;
+  sym.max_rowlen = pl.max_rowlen; sym.nblk = pl.nblk; sym.cap_blk = pl.nblk;
   sym.order = pl.order; sym.n_short = pl.n_short;
   for (int s = 0; s < 4; ++s) sym.group_need[s] = pl.group_need[s];
   sym.csr.n_rows = ga->K.n_rows; sym.csr.nnz = ga->K.nnz; sym.csr.indptr = ga->K.indptr; sym.csr.indices = ga->K.indices;

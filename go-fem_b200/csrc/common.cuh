@@ -90,6 +90,19 @@ struct femb200_ctx {
   int64_t *h_scalars = nullptr;             // pinned host mirror
   unsigned long long *h_err = nullptr;      // pinned
   cudaEvent_t ev[12] = {};
+  // second stream: the per-element checks of the fused numeric path run beside the symbolic phase
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Sizes of the previous successful call with the same mesh signature.  A call that finds a matching hint sizes its CSR
+  // arrays and launch shapes from it and does NOT wait for the device between the symbolic and the numeric phase; the
+  // kernels guard every write against the hinted capacities and the call is repeated the slow way if a guard tripped.
+  struct SizeHint {
+    bool valid = false;
+    int64_t n_nodes = -1, n_elem = -1;
+    int nn = 0, mdpn = 0, nu = 0;
+    int64_t nblk = 0;
+    int max_rowlen = 0;
+  } hint;
   // per-call scratch arena: temporaries of one add call are carved out of (normally) ONE persistent chunk, so a
   // repeated assembly performs no allocation for them and the memory pool is not churned by multi-GB temporaries
   struct ScratchChunk { char *p; size_t size; };
@@ -112,6 +125,7 @@ struct femb200_assembler {
   int32_t err_qp = -1;
   float phase_ms[FEMB200_N_TIMERS] = {};
   bool split_numeric = false; // ev[9..11] bracket k_geometry / k_rows of the last call
+  bool check_done = false;    // the per-element checks of this call already ran (second stream)
 };
 
 namespace femb200 {
@@ -191,15 +205,18 @@ struct SymbolicResult {
   int64_t n_short = 0;        // rows [0, n_short) of `order` have rowlen <= max_rowlen / 2
   int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive rows of sum(rowlen)
   int32_t *blkcols = nullptr;       // [nblk] column node of every node block
+  bool speculative = false;         // sizes came from ctx->hint: nblk / max_rowlen are capacities until the call's final sync
+  int64_t cap_blk = 0;              // capacity (node blocks) of indices / values / blkcols
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)
 };
 
 // conn32: device [n_elem*nn] validated int32 connectivity.
 int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *conn32, int64_t n_elem,
-                   SymbolicResult *out);
+                   SymbolicResult *out, bool use_hint);
 int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, int tab_doubles,
                   const int32_t *conn32, int64_t n_elem, SymbolicResult *sym, int64_t n_elem_total);
 bool numeric_supported(const ElemShape &sh);
+int check_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32, int64_t n_elem, cudaStream_t st);
 int csr_merge_into(femb200_assembler *ga, DeviceCsr *add); // K += add (consumes add)
 int csr_accumulate_rows(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
                         const double *values);

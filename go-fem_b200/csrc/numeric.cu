@@ -565,7 +565,7 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
       double4 *nodes4 = nullptr;
       if ((rc = scratch_alloc(ctx, &nodes4, (size_t)ga->n_nodes))) return rc;
       FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
-      if (n_elem) {
+      if (n_elem && !ga->check_done) {                           // normally done already, on the second stream (api.cu)
         k_geometry<D, NN, BKIND, TAB_CONST, false><<<grid_for(n_elem, 128), 128, 0, ctx->stream>>>(n_elem, ga->d_nodes, conn32, nullptr, nullptr, ctx->d_err, d_tab,
                                                                                                  tl.offW, tl.offN, tl.offDN, sh.nqp);
         ctx->launches++;
@@ -576,11 +576,12 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
       a.stag = nullptr; a.degen = nullptr; a.order = nullptr; a.v0 = 0; a.v1 = ga->n_nodes; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
       a.has_halo = n_elem < n_elem_total ? 1 : 0;
       for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
-      rc = srows_fused(ctx, sh, a, ga->d_nodes, sym->blkcols, h_tab, nullptr, 0, ga->n_nodes, sym->max_rowlen, nodes4);
+      rc = srows_fused(ctx, sh, a, ga->d_nodes, sym->blkcols, h_tab, nullptr, 0, ga->n_nodes, sym->max_rowlen, nodes4, sym->cap_blk);
       FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
       if (rc != -2) { ga->split_numeric = true; return rc; }
     }
   }
+  if (sym->speculative) return -3; // hinted sizes are only safe with the guarded fused kernel: the caller repeats the call without hints
   rc = scratch_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * S::REC);
   if (rc) return rc;
   if ((rc = scratch_alloc(ctx, &degen, (size_t)n_elem))) return rc;
@@ -715,6 +716,7 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
                   const int32_t *conn32, int64_t n_elem, SymbolicResult *sym, int64_t n_elem_total) {
   femb200_ctx *ctx = ga->ctx;
   if (!numeric_supported(sh)) return FEMB200_ERR_UNSUPPORTED;
+  if (sym->speculative && !(sh.identity && sh.nn <= 4)) return -3; // hinted sizes need the guarded fused kernel
   const bool tab_const = tab_doubles <= kTabDoubles && !ctx->concurrent; // __constant__ tables are per device: one call at a time
   if (tab_const)
     FEMB_CUDA_OK(ctx, cudaMemcpyToSymbolAsync(c_tab, h_tab, sizeof(double) * tab_doubles, 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -744,6 +746,49 @@ int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_ta
     return sh.d == 3 ? dispatch_nn<3, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym, n_elem)
                      : dispatch_nn<2, FEMB200_B_THERMAL>(ga, sh, a, tab_const, sym, n_elem);
   case FEMB200_B_THERMAL_AXISYM: return dispatch_nn<2, FEMB200_B_THERMAL_AXISYM>(ga, sh, a, tab_const, sym, n_elem);
+  }
+  return FEMB200_ERR_UNSUPPORTED;
+}
+
+
+// ---- per-element checks only (assembler_isoparametric.go:95-107), for the fused numeric path ------------------------------
+// Runs k_geometry without stores on `st` (the context's second stream: beside the symbolic phase).  Tables from global memory.
+template <int D, int NN, int BKIND>
+static int launch_check(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32, int64_t n_elem, cudaStream_t st) {
+  femb200_ctx *ctx = ga->ctx;
+  using B = BT<BKIND, D>;
+  if (sh.ndn != B::NDN || sh.dimC != B::DIMC) return FEMB200_ERR_UNSUPPORTED;
+  TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
+  if (n_elem) {
+    k_geometry<D, NN, BKIND, false, false><<<grid_for(n_elem, 128), 128, 0, st>>>(n_elem, ga->d_nodes, conn32, nullptr, nullptr, ctx->d_err, d_tab,
+                                                                                 tl.offW, tl.offN, tl.offDN, sh.nqp);
+    ctx->launches++;
+  }
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+template <int D, int BKIND>
+static int check_nn(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32, int64_t n_elem, cudaStream_t st) {
+#define FEMB_C(NNV) return launch_check<D, NNV, BKIND>(ga, sh, d_tab, conn32, n_elem, st)
+  if constexpr (D == 3) {
+    switch (sh.nn) { case 4: FEMB_C(4); case 8: FEMB_C(8); case 10: FEMB_C(10); case 20: FEMB_C(20); }
+  } else {
+    switch (sh.nn) { case 3: FEMB_C(3); case 4: FEMB_C(4); case 8: FEMB_C(8); }
+  }
+#undef FEMB_C
+  return FEMB200_ERR_UNSUPPORTED;
+}
+
+int check_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32, int64_t n_elem, cudaStream_t st) {
+  if (!numeric_supported(sh)) return FEMB200_ERR_UNSUPPORTED;
+  switch (sh.bkind) {
+  case FEMB200_B_XYZ: return check_nn<3, FEMB200_B_XYZ>(ga, sh, d_tab, conn32, n_elem, st);
+  case FEMB200_B_PLANE: return check_nn<2, FEMB200_B_PLANE>(ga, sh, d_tab, conn32, n_elem, st);
+  case FEMB200_B_AXISYM: return check_nn<2, FEMB200_B_AXISYM>(ga, sh, d_tab, conn32, n_elem, st);
+  case FEMB200_B_THERMAL:
+    return sh.d == 3 ? check_nn<3, FEMB200_B_THERMAL>(ga, sh, d_tab, conn32, n_elem, st) : check_nn<2, FEMB200_B_THERMAL>(ga, sh, d_tab, conn32, n_elem, st);
+  case FEMB200_B_THERMAL_AXISYM: return check_nn<2, FEMB200_B_THERMAL_AXISYM>(ga, sh, d_tab, conn32, n_elem, st);
   }
   return FEMB200_ERR_UNSUPPORTED;
 }

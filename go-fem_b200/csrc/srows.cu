@@ -362,6 +362,8 @@ struct FusedIn {
   const double4 *nodes4;                // [n_nodes] (x, y, z, 0)
   const int32_t *blkcols;               // ascending column nodes of row I at blkcols[blkptr[I] ...]
   int rl_cap;
+  int64_t cap_blk;                      // capacity (node blocks) of values / blkcols: guards a call sized from a hint
+  unsigned long long *guard;            // set when a row does not fit the hinted sizes (the call is then repeated)
 };
 
 template <int D> __device__ __forceinline__ double inv_lean(const double (&J)[D][D], double (&inv)[D][D]);
@@ -421,30 +423,28 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
     b0 = __ldg(a.blkptr + I);
     rl = (int)(__ldg(a.blkptr + I + 1) - b0);
   }
+  if (rl > fi.rl_cap || b0 + rl > fi.cap_blk) {              // sizes came from a hint and this row does not fit
+    if (i == 0) atomicOr(fi.guard, 1ull);
+    rl = 0;
+  }
   if (rl == 0) end = beg;
   const int rowsz = rl * NDN;
   double *const acc = acc_w + lane;
   constexpr int AS = 32;                                         // accumulator stride
   for (int m = 0; m < rowsz; ++m) acc[m * AS] = 0.0;
 
-  // coordinate cache of my node row: xs[p][0..D) = coordinates of column node p (the NDN lanes of the row share the gathers)
+  // coordinate cache of my node row: xs[p][0..D) = coordinates of column node p (the NDN lanes of the row share the
+  // gathers); the simplex path caches the edge vectors X[p] - X[I] instead, which is all it ever needs
   double *const xs = s_stage + (size_t)r * fi.rl_cap * D;
-  double X0[D];                                                  // my own node
-#pragma unroll
-  for (int j = 0; j < D; ++j) X0[j] = 0.0;
   if (rl) {
+    double X0[4] = {0.0, 0.0, 0.0, 0.0};
+    if constexpr (SIMPLEX) ld256(reinterpret_cast<const double *>(fi.nodes4 + I), X0);
     const int32_t *cols = fi.blkcols + b0;
     for (int p = i; p < rl; p += NDN) {
       double c4[4];
       ld256(reinterpret_cast<const double *>(fi.nodes4 + __ldg(cols + p)), c4);
 #pragma unroll
-      for (int j = 0; j < D; ++j) xs[p * D + j] = c4[j];
-    }
-    if constexpr (SIMPLEX) {
-      double c4[4];
-      ld256(reinterpret_cast<const double *>(fi.nodes4 + I), c4);
-#pragma unroll
-      for (int j = 0; j < D; ++j) X0[j] = c4[j];
+      for (int j = 0; j < D; ++j) xs[p * D + j] = c4[j] - X0[j];
     }
   }
   __syncwarp();
@@ -487,53 +487,52 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
         if (b >= NN) b -= NN;
         pr[bp] = (int)((w64 >> (16 * b)) & kPosMask);
       }
-      double ed[D][D];                                           // edge vectors e_k = X[k] - X[0], k = 1..D
+      double ed[D][D];                                           // edge vectors e_k = X[k] - X[0], k = 1..D (cached)
 #pragma unroll
       for (int kk = 0; kk < D; ++kk) {
         const double *xp = xs + pr[kk + 1] * D;
 #pragma unroll
-        for (int j = 0; j < D; ++j) ed[kk][j] = xp[j] - X0[j];
+        for (int j = 0; j < D; ++j) ed[kk][j] = xp[j];
       }
-      double g[NN][D], det;
+      // c[b'] = det * grad N_b' (unscaled): cross products of edges (3-D) / rotated edges (2-D); c[0] = -(sum of the others)
+      double c[NN][D], det;
       if constexpr (D == 3) {
-        double c[3][3];
 #pragma unroll
         for (int kk = 0; kk < 3; ++kk) {
           const int k1 = (kk + 1) % 3, k2 = (kk + 2) % 3;
-          c[kk][0] = fma(ed[k1][1], ed[k2][2], -(ed[k1][2] * ed[k2][1]));
-          c[kk][1] = fma(ed[k1][2], ed[k2][0], -(ed[k1][0] * ed[k2][2]));
-          c[kk][2] = fma(ed[k1][0], ed[k2][1], -(ed[k1][1] * ed[k2][0]));
+          c[kk + 1][0] = fma(ed[k1][1], ed[k2][2], -(ed[k1][2] * ed[k2][1]));
+          c[kk + 1][1] = fma(ed[k1][2], ed[k2][0], -(ed[k1][0] * ed[k2][2]));
+          c[kk + 1][2] = fma(ed[k1][0], ed[k2][1], -(ed[k1][1] * ed[k2][0]));
         }
-        det = fma(ed[0][0], c[0][0], fma(ed[0][1], c[0][1], ed[0][2] * c[0][2]));
-        const double rd = 1.0 / det;
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) g[kk + 1][j] = c[kk][j] * rd;
-        if (la & 1) det = -det;                                  // odd shift of 4 vertices: orientation flips
+        det = fma(ed[0][0], c[1][0], fma(ed[0][1], c[1][1], ed[0][2] * c[1][2]));
       } else {
         det = fma(ed[0][0], ed[1][1], -(ed[0][1] * ed[1][0]));
-        const double rd = 1.0 / det;
-        g[1][0] = ed[1][1] * rd; g[1][1] = -ed[1][0] * rd;
-        g[2][0] = -ed[0][1] * rd; g[2][1] = ed[0][0] * rd;
+        c[1][0] = ed[1][1]; c[1][1] = -ed[1][0];
+        c[2][0] = -ed[0][1]; c[2][1] = ed[0][0];
       }
+      const double rd = 1.0 / det;                               // off the critical path: only the final scaling of E needs it
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        double sg = g[1][j];
+        double sg = c[1][j];
 #pragma unroll
-        for (int kk = 2; kk < NN; ++kk) sg += g[kk][j];
-        g[0][j] = -sg;
+        for (int kk = 2; kk < NN; ++kk) sg += c[kk][j];
+        c[0][j] = -sg;
       }
-      const double f = det * tb.w[0];                            // (dJac*w)*scale with scale = 1 (:111)
+      // u = f * grad N_a = (det_nat * w) * c[0] / det = +-w * c[0]: a cyclic shift of 4 vertices by an odd count flips the
+      // orientation (det = -det_nat), a shift of 3 vertices never does
+      double ws = tb.w[0];                                       // (dJac*w)*scale with scale = 1 (:111)
+      if (D == 3 && (la & 1)) ws = -ws;
       double E[DIMC];
 #pragma unroll
-      for (int c = 0; c < DIMC; ++c) E[c] = 0.0;
+      for (int cc = 0; cc < DIMC; ++cc) E[cc] = 0.0;
 #pragma unroll
       for (int m = 0; m < NV; ++m) {
-        const double u = g[0][m] * f;
+        const double u = c[0][m] * ws;
 #pragma unroll
-        for (int c = 0; c < DIMC; ++c) E[c] = fma(u, Ci[m][c], E[c]);
+        for (int cc = 0; cc < DIMC; ++cc) E[cc] = fma(u, Ci[m][cc], E[cc]);
       }
+#pragma unroll
+      for (int cc = 0; cc < DIMC; ++cc) E[cc] *= rd;             // E = f * B_a[:, i]^T C / det: the blocks below use the unscaled c
 #pragma unroll
       for (int bp = 0; bp < NN; ++bp) {
         double bl[NDN];
@@ -542,7 +541,7 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
           double sb = 0.0;
 #pragma unroll
           for (int kk = 0; kk < DIMC; ++kk)
-            if (B::sel(kk, j) >= 0) sb = fma(E[kk], g[bp][B::sel(kk, j)], sb);
+            if (B::sel(kk, j) >= 0) sb = fma(E[kk], c[bp][B::sel(kk, j)], sb);
           bl[j] = sb;
         }
         if (bp == 0) {
@@ -718,12 +717,13 @@ static int launch_fused_T(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &
 
 // fused front end for elements with <= 4 nodes; returns -2 when it does not apply
 int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *blkcols,
-                const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4) {
+                const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4, int64_t cap_blk) {
   if (sh.nn > 4) return -2;
   k_pad_nodes<<<grid_for(a.n_nodes, 256), 256, 0, ctx->stream>>>(a.n_nodes, d_nodes, nodes4);
   ctx->launches++;
   FusedIn fi;
   fi.nodes4 = nodes4; fi.blkcols = blkcols; fi.rl_cap = 0;
+  fi.cap_blk = cap_blk; fi.guard = (unsigned long long *)(ctx->d_scalars + 7);
   const bool t64 = !(getenv("FEMB200_SROW_TPB") && atoi(getenv("FEMB200_SROW_TPB")) == 128); // 64-thread blocks: finer shared-memory granularity
 #define FEMB_F(Dv, NNv, BK) return t64 ? launch_fused_T<Dv, NNv, BK, 64>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap) : launch_fused_T<Dv, NNv, BK, 128>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap)
   switch (sh.bkind) {

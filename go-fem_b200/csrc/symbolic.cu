@@ -27,7 +27,8 @@ __global__ void k_narrow_validate(const IntT *__restrict__ in, int32_t *__restri
   if (t >= n) return;
   long long v = (long long)in[t];
   if (v < 0 || v >= n_nodes) {
-    atomicMin(err, pack_error(t / nn, 0, FEMB200_ERR_NODE_OOB));
+    atomicMin(err, pack_error(t / nn, 0, 0)); // kind 0 in the device word = node out of range: beats every geometry error of the SAME
+                                              // element (the reference panics while gathering the coordinates, before the Jacobian)
     v = 0;
   }
   out[t] = (int32_t)v;
@@ -379,7 +380,7 @@ template <int NU, int LPN>
 __global__ void __launch_bounds__(256)
 k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ umap_packed, const int32_t *__restrict__ n2e_ptr,
          const int64_t *__restrict__ blkptr, const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices,
-         const int32_t *__restrict__ col_map, int32_t *__restrict__ blkcols) {
+         const int32_t *__restrict__ col_map, int32_t *__restrict__ blkcols, int64_t cap_blk, unsigned long long *__restrict__ guard) {
   const int nu = NU > 0 ? NU : nu_rt;
   const int lane = threadIdx.x & (LPN - 1);
   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPN;
@@ -387,6 +388,7 @@ k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ u
   const int64_t b0 = blkptr[I];
   const int rl = (int)(blkptr[I + 1] - b0);
   if (rl == 0) return;
+  if (b0 + rl > cap_blk) { if (lane == 0) atomicOr(guard, 1ull); return; } // hinted capacity exceeded: the call is repeated
   const int32_t *cols = tmpcols + (int64_t)nn * n2e_ptr[I];
   const int rowsz = rl * nu;
   int um[NU > 0 ? NU : kMaxNdn];
@@ -456,7 +458,7 @@ static int ensure_cub_tmp(femb200_ctx *ctx, size_t bytes) {
 }
 
 int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *conn32, int64_t n_elem,
-                   SymbolicResult *out) {
+                   SymbolicResult *out, bool use_hint) {
   femb200_ctx *ctx = ga->ctx;
   cudaStream_t st = ctx->stream;
   const int nn = sh.nn;
@@ -542,13 +544,22 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], st));
-  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
-  out->max_rowlen = (int)ctx->h_scalars[0];
-  out->nblk = ctx->h_scalars[1];
-  for (int s = 0; s < 4; ++s) out->group_need[s] = n_nodes ? ctx->h_scalars[2 + s] : 0;
-  if (out->order) out->n_short = ctx->h_scalars[6];
-  if (*ctx->h_err != kNoError) return -1; // caller decodes the error word
-  if (out->max_rowlen > (int)pos_mask(nn)) return FEMB200_ERR_TOO_LARGE;
+  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(int64_t), st)); // capacity-guard flag
+  if (use_hint) {
+    // sizes from the previous call with this mesh signature; verified by the caller after the call's only synchronisation
+    out->speculative = true;
+    out->max_rowlen = ctx->hint.max_rowlen;
+    out->nblk = ctx->hint.nblk;
+  } else {
+    FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    out->max_rowlen = (int)ctx->h_scalars[0];
+    out->nblk = ctx->h_scalars[1];
+    for (int s = 0; s < 4; ++s) out->group_need[s] = n_nodes ? ctx->h_scalars[2 + s] : 0;
+    if (out->order) out->n_short = ctx->h_scalars[6];
+    if (*ctx->h_err != kNoError) return -1; // caller decodes the error word
+    if (out->max_rowlen > (int)pos_mask(nn)) return FEMB200_ERR_TOO_LARGE;
+  }
+  out->cap_blk = out->nblk;
 
   // ---- scalar CSR pattern ----------------------------------------------------------------------
   const int nu = sh.nu;
@@ -573,8 +584,8 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
     const unsigned eg = grid_for(n_nodes * (small ? 8 : 32), 256);
 #define FEMB_EXPAND(NUV)                                                                                                          \
   do {                                                                                                                          \
-    if (small) k_expand<NUV, 8><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map, out->blkcols); \
-    else k_expand<NUV, 32><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map, out->blkcols);   \
+    if (small) k_expand<NUV, 8><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map, out->blkcols, out->cap_blk, (unsigned long long *)(ctx->d_scalars + 7)); \
+    else k_expand<NUV, 32><<<eg, 256, 0, st>>>(n_nodes, nn, sh.mdpn, nu, d_umap, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, ga->d_col_map, out->blkcols, out->cap_blk, (unsigned long long *)(ctx->d_scalars + 7));   \
   } while (0)
     switch (nu) {
     case 1: FEMB_EXPAND(1); break;

@@ -186,6 +186,36 @@ def test_fixture_meshes(pkg, O):
 
 
 # ---- error behaviour -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("elem", ["tetra4", "hexa8"])
+def test_two_faults_follow_the_sequential_loop(pkg, meshes, elem):
+    """fem.go:140 walks the elements in order: with an inverted element and an out-of-range node in ONE mesh the
+    reference reports whichever comes first (the Jacobian error of #3 before the slice panic of #10, and vice versa).
+    Tetra4 takes the fused path (checks on the second stream), Hexa8 the staged one (checks over the leading elements)."""
+    if elem == "tetra4":
+        nodes, conn = meshes.bcc_tetra4(3)
+        et, swap = pkg.elements.Tetra4(), [2, 3]
+    else:
+        nodes, conn = meshes.hexa8_grid(4, 4, 4)
+        et, swap = pkg.elements.Hexa8(), [0, 6]
+    c = pkg.solids.Isotropic(200e9, 0.3).Solid3D()
+    a = conn.copy()
+    a[3, swap] = a[3, swap[::-1]]
+    a[10, 1] = nodes.shape[0]
+    err = pkg.fem.NewGeneralAssembler(nodes, 7).AddIsoparametric(et, c, len(a), a)
+    assert err is not None and not err.is_panic and "element #3" in err.msg
+    b = conn.copy()
+    b[3, 1] = nodes.shape[0] + 5
+    b[10, swap] = b[10, swap[::-1]]
+    err = pkg.fem.NewGeneralAssembler(nodes, 7).AddIsoparametric(et, c, len(b), b)
+    assert err is not None and err.is_panic and "#3" in err.msg
+    # the same element both inverted and out of range: the gather panics before the Jacobian exists
+    d = conn.copy()
+    d[7, swap] = d[7, swap[::-1]]
+    d[7, 2] = -1
+    err = pkg.fem.NewGeneralAssembler(nodes, 7).AddIsoparametric(et, c, len(d), d)
+    assert err is not None and err.is_panic and "#7" in err.msg
+
 def test_errors_report_lowest_element_and_leave_k_untouched(pkg, O, meshes):
     nodes, conn = meshes.bcc_tetra4(4)
     bad = conn.copy()
