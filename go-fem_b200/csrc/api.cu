@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <cstring>
 #include <vector>
+#include <functional>
 
 using namespace femb200;
 
@@ -187,7 +188,7 @@ static int decode_error(femb200_assembler *ga) {
 
 // uploads (if needed), narrows to int32 and validates the connectivity
 static int stage_conn(femb200_assembler *ga, const void *conn, bool is64, bool on_device, int64_t n, int nn,
-                      int32_t **conn32, void **staged) {
+                      int32_t **conn32, void **staged, int32_t *cnt = nullptr, bool agg = false) {
   femb200_ctx *ctx = ga->ctx;
   *staged = nullptr;
   int rc;
@@ -201,7 +202,7 @@ static int stage_conn(femb200_assembler *ga, const void *conn, bool is64, bool o
     FEMB_CUDA_OK(ctx, cudaMemcpyAsync(*staged, conn, bytes, cudaMemcpyHostToDevice, ctx->stream));
     d_in = *staged;
   }
-  return narrow_and_validate_conn(ga, d_in, is64, n, nn, *conn32);
+  return narrow_and_validate_conn(ga, d_in, is64, n, nn, *conn32, cnt, agg);
 }
 
 int femb200_add_isoparametric(femb200_assembler *ga, const femb200_elem_desc *desc, const void *conn,
@@ -252,7 +253,12 @@ static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     return code;
   };
-  rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged);
+  // the incidence histogram of the adjacency is taken in the pass that narrows / validates the connectivity
+  int32_t *precount = nullptr;
+  rc = scratch_alloc(ctx, &precount, (size_t)2 * (ga->n_nodes + 1));
+  if (!rc && cudaMemsetAsync(precount, 0, sizeof(int32_t) * 2 * (ga->n_nodes + 1), st) != cudaSuccess) { ctx->last_cuda_error = "cudaMemsetAsync"; rc = FEMB200_ERR_CUDA; }
+  if (!rc) rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged, precount, sh.nn == 4 && sh.d == 3);
+  sym.precount = precount;
   if (!rc) rc = scratch_alloc(ctx, &d_tab, blob.size());
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st);
@@ -264,23 +270,26 @@ static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc
   // the reference's per-element checks (:95-107) do not depend on the pattern: on the fused path they run on the second
   // stream, beside the symbolic phase (FP64 work beside atomics / integer work)
   bool forked = false;
-  if (fused_ok && ctx->stream2 && n_elem - n_pattern_only > 0 && !getenv("FEMB200_NO_FORK")) {
+  std::function<int()> fork_fn = [&]() -> int {
     cudaError_t e = cudaEventRecord(ctx->ev_fork, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
-    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); return fail(FEMB200_ERR_CUDA); }
-    rc = check_phase(ga, sh, d_tab, conn32, n_elem - n_pattern_only, ctx->stream2);
-    if (rc == 0) {
-      e = cudaEventRecord(ctx->ev_join, ctx->stream2);
-      if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); return fail(FEMB200_ERR_CUDA); }
-      forked = true;
-      ga->check_done = true;
-    } else if (rc != FEMB200_ERR_UNSUPPORTED) {
-      return fail(rc);
-    }
-    rc = 0;
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); return FEMB200_ERR_CUDA; }
+    int r2 = check_phase(ga, sh, d_tab, conn32, n_elem - n_pattern_only, ctx->stream2);
+    if (r2 == FEMB200_ERR_UNSUPPORTED) return 0;
+    if (r2) return r2;
+    e = cudaEventRecord(ctx->ev_join, ctx->stream2);
+    if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); return FEMB200_ERR_CUDA; }
+    forked = true;
+    ga->check_done = true;
+    return 0;
+  };
+  int fork_at = 0;
+  if (fused_ok && ctx->stream2 && n_elem - n_pattern_only > 0 && !getenv("FEMB200_NO_FORK")) {
+    fork_at = getenv("FEMB200_FORK_AT") ? atoi(getenv("FEMB200_FORK_AT")) : 2; // beside the row-pattern kernel (integer work)
+    if (fork_at == 1 && (rc = fork_fn())) return fail(rc);
   }
 
-  rc = symbolic_phase(ga, sh, conn32, n_elem, &sym, use_hint); // synchronises once unless sized from the hint
+  rc = symbolic_phase(ga, sh, conn32, n_elem, &sym, use_hint, fork_at, &fork_fn); // synchronises once unless sized from the hint
   if (rc == -1) {
     // a node index is out of range.  The reference's loop is sequential (fem.go:140): an element BEFORE the offending one
     // may fail its Jacobian checks first, so those checks run over the elements in front of it and the lowest word wins.

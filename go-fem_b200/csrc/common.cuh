@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <functional>
 #include "../../include/femb200.h"
 
 namespace femb200 {
@@ -205,14 +206,17 @@ struct SymbolicResult {
   int64_t n_short = 0;        // rows [0, n_short) of `order` have rowlen <= max_rowlen / 2
   int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive rows of sum(rowlen)
   int32_t *blkcols = nullptr;       // [nblk] column node of every node block
+  int32_t *precount = nullptr;      // [2*(n_nodes+1)] incidence histogram | zeroed fill cursors, taken while narrowing (or NULL)
   bool speculative = false;         // sizes came from ctx->hint: nblk / max_rowlen are capacities until the call's final sync
   int64_t cap_blk = 0;              // capacity (node blocks) of indices / values / blkcols
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)
 };
 
 // conn32: device [n_elem*nn] validated int32 connectivity.
+// fork_at / fork_fn: the caller's side-stream work (per-element checks) is started after the adjacency (2) or after the row
+// pattern (3) has been queued
 int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *conn32, int64_t n_elem,
-                   SymbolicResult *out, bool use_hint);
+                   SymbolicResult *out, bool use_hint, int fork_at = 0, const std::function<int()> *fork_fn = nullptr);
 int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, int tab_doubles,
                   const int32_t *conn32, int64_t n_elem, SymbolicResult *sym, int64_t n_elem_total);
 bool numeric_supported(const ElemShape &sh);
@@ -231,7 +235,7 @@ int csr_add_entries_async(femb200_assembler *ga, int64_t n_rows, const int64_t *
 int strains_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32,
                   int64_t n_elem, const int32_t *d_dofmap, const double *d_u, double *d_strains);
 int narrow_and_validate_conn(femb200_assembler *ga, const void *d_conn_in, bool is64, int64_t n, int nn,
-                             int32_t *conn32_out);
+                             int32_t *conn32_out, int32_t *cnt = nullptr, bool agg = false);
 int slot_map(femb200_assembler *ga, int64_t *d_slot);
 int probe_peaks(femb200_ctx *ctx, int reps, double out[2]);
 int csr_slice(femb200_assembler *ga, int64_t n_rows, const int64_t *h_rows, int64_t n_cols, const int64_t *h_cols, int64_t *h_indptr,

@@ -20,9 +20,10 @@
 namespace femb200 {
 
 // ------------------------------------------------------------------------------------------------
-template <class IntT>
+// cnt != NULL: the incidence histogram of the adjacency (k_count_incidence) is taken in the same pass; AGG as there.
+template <class IntT, bool AGG>
 __global__ void k_narrow_validate(const IntT *__restrict__ in, int32_t *__restrict__ out, int64_t n, int nn,
-                                  int64_t n_nodes, unsigned long long *err) {
+                                  int64_t n_nodes, unsigned long long *err, int32_t *__restrict__ cnt) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   long long v = (long long)in[t];
@@ -32,15 +33,28 @@ __global__ void k_narrow_validate(const IntT *__restrict__ in, int32_t *__restri
     v = 0;
   }
   out[t] = (int32_t)v;
+  if (cnt) {
+    const int32_t node = (int32_t)v;
+    if constexpr (AGG) {
+      const unsigned peers = __match_any_sync(__activemask(), node);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[node], __popc(peers));
+    } else {
+      atomicAdd(&cnt[node], 1);
+    }
+  }
 }
 
-int narrow_and_validate_conn(femb200_assembler *ga, const void *d_in, bool is64, int64_t n, int nn, int32_t *out) {
+int narrow_and_validate_conn(femb200_assembler *ga, const void *d_in, bool is64, int64_t n, int nn, int32_t *out, int32_t *cnt, bool agg) {
   femb200_ctx *ctx = ga->ctx;
   if (n == 0) return 0;
-  if (is64)
-    k_narrow_validate<long long><<<grid_for(n, 256), 256, 0, ctx->stream>>>((const long long *)d_in, out, n, nn, ga->n_nodes, ctx->d_err);
-  else
-    k_narrow_validate<int32_t><<<grid_for(n, 256), 256, 0, ctx->stream>>>((const int32_t *)d_in, out, n, nn, ga->n_nodes, ctx->d_err);
+  const unsigned g = grid_for(n, 256);
+  if (is64) {
+    if (agg) k_narrow_validate<long long, true><<<g, 256, 0, ctx->stream>>>((const long long *)d_in, out, n, nn, ga->n_nodes, ctx->d_err, cnt);
+    else k_narrow_validate<long long, false><<<g, 256, 0, ctx->stream>>>((const long long *)d_in, out, n, nn, ga->n_nodes, ctx->d_err, cnt);
+  } else {
+    if (agg) k_narrow_validate<int32_t, true><<<g, 256, 0, ctx->stream>>>((const int32_t *)d_in, out, n, nn, ga->n_nodes, ctx->d_err, cnt);
+    else k_narrow_validate<int32_t, false><<<g, 256, 0, ctx->stream>>>((const int32_t *)d_in, out, n, nn, ga->n_nodes, ctx->d_err, cnt);
+  }
   ctx->launches++;
   FEMB_CUDA_OK(ctx, cudaGetLastError());
   return 0;
@@ -176,7 +190,7 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   constexpr int G = 8, MAXINC = G * IPL; // IPL incidences per lane: rows with more than 8*IPL incidences take the fallback
   constexpr int CAP = HS * 3 / 4;
   constexpr int LOG = HS == 32 ? 5 : (HS == 64 ? 6 : 7);
-  constexpr int GW = HS + HS + MAXINC + CAP; // 32-bit words of shared memory per group
+  constexpr int GW = HS + HS + MAXINC + ((CAP + 4 + 3) & ~3); // 32-bit words of shared memory per group (every part a multiple of 4: 16-byte loads)
   extern __shared__ int32_t s_mem[];
   const int tid = threadIdx.x, l = tid & (G - 1);
   int32_t *keys = s_mem + (tid / G) * GW;
@@ -193,23 +207,31 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   const int m = end - beg;
   if (m > MAXINC) { if (l == 0) rowlen[I] = -1; return; }
 
-  // 1. incidences, sorted
+  // 1. incidences, sorted (rank counting against the whole list, four list entries per shared-memory load)
   uint32_t tv[IPL];
 #pragma unroll
   for (int s = 0; s < IPL; ++s) {
     const int idx = l + G * s;
     tv[s] = idx < m ? n2e_t[beg + idx] : 0xffffffffu;
-    if (idx < m) lst[idx] = tv[s];
+    lst[idx] = tv[s];                                            // MAXINC entries: the tail is padding that ranks above everything
   }
   __syncwarp(gmask);
+  {
+    int rr[IPL];
 #pragma unroll
-  for (int s = 0; s < IPL; ++s) {
-    if (l + G * s < m) {
-      int r = 0;
-      for (int j = 0; j < m; ++j) r += lst[j] < tv[s];
-      rk[r] = (int32_t)tv[s];
-      n2e_t[beg + r] = tv[s];
+    for (int s = 0; s < IPL; ++s) rr[s] = 0;
+    const uint4 *l4 = reinterpret_cast<const uint4 *>(lst);
+    for (int j = 0; j < (m + 3) / 4; ++j) {
+      const uint4 w = l4[j];
+#pragma unroll
+      for (int s = 0; s < IPL; ++s) rr[s] += (w.x < tv[s]) + (w.y < tv[s]) + (w.z < tv[s]) + (w.w < tv[s]);
     }
+#pragma unroll
+    for (int s = 0; s < IPL; ++s)
+      if (l + G * s < m) {
+        rk[rr[s]] = (int32_t)tv[s];
+        n2e_t[beg + rr[s]] = tv[s];
+      }
   }
   __syncwarp(gmask);
 #pragma unroll
@@ -235,7 +257,8 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
     }
   }
 
-  // 3. hash insert
+  // 3. hash insert (shared-memory atomicCAS; a lock-step variant with plain stores and a re-read after a group barrier was
+  // measured at twice the time of this kernel: two barriers per probe cost more than the atomic)
   for (int h = l; h < HS; h += G) keys[h] = -1;
   __syncwarp(gmask);
   bool ovf = false;
@@ -248,8 +271,10 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
         unsigned h = ((unsigned)J * 0x9E3779B1u) >> (32 - LOG);
         int probe = 0;
         for (; probe < HS; ++probe) {
-          const int32_t old = atomicCAS(&keys[h], -1, J);
-          if (old == -1 || old == J) break;
+          // most candidates are duplicates (every neighbour shows up in 4-6 incident elements): look before the atomic
+          int32_t cur = *reinterpret_cast<volatile int32_t *>(&keys[h]);
+          if (cur == -1) cur = atomicCAS(&keys[h], -1, J);
+          if (cur == -1 || cur == J) break;
           h = (h + 1) & (HS - 1);
         }
         ovf = ovf || (probe == HS);
@@ -271,17 +296,26 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   }
   ovf = __any_sync(gmask, ovf) || cnt > CAP;
   if (ovf) { if (l == 0) rowlen[I] = -1; return; }
+  if (l < 4 && cnt + l < CAP + 4) ul[cnt + l] = 0x7fffffff;       // padding for the four-wide rank loop (ul holds CAP + 4 words)
   __syncwarp(gmask);
   int32_t *gcols = tmpcols + (int64_t)NN * beg;
+  {
+    int32_t key[HS / G];
+    int rr[HS / G];
 #pragma unroll
-  for (int s = 0; s < HS / G; ++s) {
-    const int32_t key = keys[s * G + l];
-    if (key >= 0) {
-      int r = 0;
-      for (int j = 0; j < cnt; ++j) r += ul[j] < key;
-      rk[s * G + l] = r;
-      gcols[r] = key;
+    for (int s = 0; s < HS / G; ++s) { key[s] = keys[s * G + l]; rr[s] = 0; }
+    const int4 *u4 = reinterpret_cast<const int4 *>(ul);
+    for (int j = 0; j < (cnt + 3) / 4; ++j) {
+      const int4 w = u4[j];
+#pragma unroll
+      for (int s = 0; s < HS / G; ++s) rr[s] += (w.x < key[s]) + (w.y < key[s]) + (w.z < key[s]) + (w.w < key[s]);
     }
+#pragma unroll
+    for (int s = 0; s < HS / G; ++s)
+      if (key[s] >= 0) {
+        rk[s * G + l] = rr[s];
+        gcols[rr[s]] = key[s];
+      }
   }
   __syncwarp(gmask);
 
@@ -407,6 +441,62 @@ k_expand(int64_t n_nodes, int nn, int mdpn, int nu_rt, const int *__restrict__ u
   }
 }
 
+// Expansion for the common case (identity dof map, rows of <= 32 node blocks): a warp takes EIGHT consecutive node rows.
+// The row metadata of all eight is fetched by parallel lanes and every row's column list sits in a register of lane p,
+// so a warp pays two memory round trips per eight rows instead of three per row (k_expand is bound by exactly that
+// latency); it also writes the scalar row pointers of its rows (k_indptr) and the compact block-column list of the plan.
+template <int NU>
+__global__ void __launch_bounds__(256)
+k_expand8(int64_t n_nodes, int nn, const int32_t *__restrict__ n2e_ptr, const int64_t *__restrict__ blkptr,
+          const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices, int64_t *__restrict__ indptr,
+          const int32_t *__restrict__ col_map, int32_t *__restrict__ blkcols, int64_t cap_blk, unsigned long long *__restrict__ guard) {
+  constexpr int R = 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t I0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R;
+  if (I0 >= n_nodes) return;
+  const int nrow = (int)(n_nodes - I0 < R ? n_nodes - I0 : R);
+  int64_t bp = 0;
+  int np = 0;
+  if (lane <= nrow) bp = __ldg(blkptr + I0 + lane);
+  if (lane < nrow) np = __ldg(n2e_ptr + I0 + lane);
+  const int64_t bp_next = __shfl_down_sync(0xffffffffu, bp, 1);
+  const int rl_mine = lane < nrow ? (int)(bp_next - bp) : 0;     // lane r: length of row I0 + r
+  // scalar row pointers: row (I0 + r, i) starts at NU*NU*bp_r + i*rl_r*NU
+  if (lane < nrow) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) indptr[(I0 + lane) * NU + i] = (int64_t)NU * NU * bp + (int64_t)i * rl_mine * NU;
+  }
+  if (I0 + nrow == n_nodes && lane == nrow) indptr[n_nodes * NU] = (int64_t)NU * NU * bp;
+  const bool over = lane < nrow && bp + rl_mine > cap_blk;
+  if (__any_sync(0xffffffffu, over)) { if (lane == 0) atomicOr(guard, 1ull); return; } // hinted capacity exceeded: the call is repeated
+  int32_t colreg[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int rl = __shfl_sync(0xffffffffu, rl_mine, r);
+    const int npr = __shfl_sync(0xffffffffu, np, r);
+    colreg[r] = (r < nrow && lane < rl) ? __ldg(tmpcols + (int64_t)nn * npr + lane) : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int rl = __shfl_sync(0xffffffffu, rl_mine, r);
+    const int64_t b0 = __shfl_sync(0xffffffffu, bp, r);
+    if (r >= nrow || rl == 0) continue;
+    if (lane < rl) blkcols[b0 + lane] = colreg[r];
+    const int32_t cg = col_map ? __ldg(col_map + colreg[r]) : colreg[r];
+    const int rowsz = rl * NU;
+    int32_t *out = indices + (int64_t)NU * NU * b0;
+    for (int base = 0; base < rowsz; base += 32) {               // warp-uniform trip count: every lane takes part in the shuffle
+      const int idx = base + lane;
+      const int p = idx / NU, uc = idx - p * NU;
+      const int32_t c = __shfl_sync(0xffffffffu, cg, p & 31) * NU + uc;
+      if (idx < rowsz) {
+#pragma unroll
+        for (int ur = 0; ur < NU; ++ur) out[ur * rowsz + idx] = c;
+      }
+    }
+  }
+}
+
 template <int NN>
 static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *n2e_ptr, uint32_t *n2e_t,
                               const int32_t *conn, int32_t *tmpcols, int64_t *rowlen, uint16_t *pos16, const uint8_t *node_mask) {
@@ -420,7 +510,7 @@ static int launch_row_pattern(femb200_ctx *ctx, int64_t n_nodes, const int32_t *
     constexpr int T = NN >= 8 ? 128 : 256;
     auto launch = [&](auto ipl_c, int only_flagged) -> int {
       constexpr int IPL = decltype(ipl_c)::value;
-      constexpr int GW = HS + HS + 8 * IPL + HS * 3 / 4;
+      constexpr int GW = HS + HS + 8 * IPL + ((HS * 3 / 4 + 4 + 3) & ~3);
       const size_t smem = (size_t)(T / 8) * GW * sizeof(int32_t);
       auto kern = k_row_pattern_group<NN, HS, IPL, T>;
       FEMB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -458,7 +548,7 @@ static int ensure_cub_tmp(femb200_ctx *ctx, size_t bytes) {
 }
 
 int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *conn32, int64_t n_elem,
-                   SymbolicResult *out, bool use_hint) {
+                   SymbolicResult *out, bool use_hint, int fork_at, const std::function<int()> *fork_fn) {
   femb200_ctx *ctx = ga->ctx;
   cudaStream_t st = ctx->stream;
   const int nn = sh.nn;
@@ -468,13 +558,14 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   int rc;
 
   // ---- node -> element adjacency -------------------------------------------------------------
-  int32_t *cnt = nullptr;
-  if ((rc = scratch_alloc(ctx, &cnt, 2 * (n_nodes + 1)))) return rc; // histogram | fill cursors
+  int32_t *cnt = out->precount;                                  // histogram taken while narrowing the connectivity (api.cu)?
+  const bool counted = cnt != nullptr;
+  if (!counted && (rc = scratch_alloc(ctx, &cnt, 2 * (n_nodes + 1)))) return rc; // histogram | fill cursors
   int32_t *cursor = cnt + (n_nodes + 1);
   if ((rc = dev_alloc(ctx, &out->n2e_ptr, n_nodes + 1))) return rc;
   if ((rc = dev_alloc(ctx, &out->n2e_t, ninc))) return rc;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, sizeof(int32_t) * 2 * (n_nodes + 1), st));
-  if (ninc) {
+  if (!counted) FEMB_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, sizeof(int32_t) * 2 * (n_nodes + 1), st));
+  if (ninc && !counted) {
     if (nn == 4 && sh.d == 3) k_count_incidence<true><<<grid_for(ninc, 256), 256, 0, st>>>(conn32, ninc, cnt);
     else k_count_incidence<false><<<grid_for(ninc, 256), 256, 0, st>>>(conn32, ninc, cnt);
     ctx->launches++;
@@ -498,6 +589,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
     ctx->launches++;
   }
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], st));
+  if (fork_at == 2 && fork_fn && (rc = (*fork_fn)())) return rc;
 
   // ---- node-block row pattern ----------------------------------------------------------------
   int32_t *tmpcols = nullptr;
@@ -544,6 +636,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], st));
+  if (fork_at == 3 && fork_fn && (rc = (*fork_fn)())) return rc;
   FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(int64_t), st)); // capacity-guard flag
   if (use_hint) {
     // sizes from the previous call with this mesh signature; verified by the caller after the call's only synchronisation
@@ -577,6 +670,17 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   int *d_umap = nullptr;
   if ((rc = scratch_alloc(ctx, &d_umap, kMaxNdn))) return rc;
   FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_umap, sh.umap, sizeof(int) * kMaxNdn, cudaMemcpyHostToDevice, st));
+  const bool expand8 = sh.identity && nu <= 3 && out->max_rowlen <= 32 && out->nblk > 0 && !getenv("FEMB200_NO_EXPAND8");
+  if (expand8) {
+    const unsigned eg = grid_for(((n_nodes + 7) / 8) * 32, 256);
+    unsigned long long *guard = (unsigned long long *)(ctx->d_scalars + 7);
+    switch (nu) {
+    case 1: k_expand8<1><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard); break;
+    case 2: k_expand8<2><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard); break;
+    default: k_expand8<3><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard); break;
+    }
+    ctx->launches++;
+  } else {
   k_indptr<<<grid_for(ndof + 1, 256), 256, 0, st>>>(n_nodes, sh.mdpn, nu, umask, out->blkptr, out->csr.indptr);
   ctx->launches++;
   if (out->nblk) {
@@ -595,6 +699,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
     }
 #undef FEMB_EXPAND
     ctx->launches++;
+  }
   }
   FEMB_CUDA_OK(ctx, cudaGetLastError());
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
