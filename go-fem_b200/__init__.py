@@ -67,6 +67,10 @@ def lib():
     L.femb200_nnz.restype = C.c_int64
     L.femb200_csr_copy.argtypes = [vp, vp, vp, vp]
     L.femb200_csr_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.femb200_bsr_blocks.argtypes = [vp]
+    L.femb200_bsr_blocks.restype = C.c_int64
+    L.femb200_bsr_copy.argtypes = [vp, vp, vp, vp]
+    L.femb200_add_coo.argtypes = [vp, C.c_int64, _i64p, _i64p, _dp]
     L.femb200_csr_at.argtypes = [vp, C.c_int64, C.c_int64, _dp]
     L.femb200_csr_matvec.argtypes = [vp, _dp, _dp]
     L.femb200_csr_slice.argtypes = [vp, C.c_int64, _i64p, C.c_int64, _i64p, _i64p, _i32p, _dp, _i64p]
@@ -527,6 +531,26 @@ class RawAssembler:
         if rc:
             raise RuntimeError(f"femb200_csr_copy -> {rc}")
         return indptr, indices, values
+
+    def bsr(self):
+        """femb200_bsr_copy: (blkptr, blkcols, values) -- K at node-block granularity."""
+        nblk = lib().femb200_bsr_blocks(self.h)
+        if nblk < 0:
+            raise RuntimeError("femb200_bsr_copy: K is not a single identity-map AddIsoparametric call")
+        n_nodes = self.total_dofs() // self.mdpn
+        blkptr = np.zeros(n_nodes + 1, dtype=np.int64)
+        blkcols = np.zeros(nblk, dtype=np.int32)
+        values = np.zeros(self.nnz(), dtype=np.float64)
+        rc = lib().femb200_bsr_copy(self.h, blkptr.ctypes.data, blkcols.ctypes.data, values.ctypes.data)
+        if rc:
+            raise RuntimeError(f"femb200_bsr_copy -> {rc}")
+        return blkptr, blkcols, values
+
+    def add_coo(self, rows, cols, vals):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        return lib().femb200_add_coo(self.h, rows.size, rows.ctypes.data_as(_i64p), cols.ctypes.data_as(_i64p), _d(vals))
 
     def csr_copy_into(self, indptr_ptr, indices_ptr, values_ptr):
         return lib().femb200_csr_copy(self.h, indptr_ptr, indices_ptr, values_ptr)

@@ -497,6 +497,25 @@ int femb200_csr_copy(const femb200_assembler *ga, int64_t *indptr, int32_t *indi
   return 0;
 }
 
+int64_t femb200_bsr_blocks(const femb200_assembler *ga) {
+  if (!ga || !ga->plan.matches_K || !ga->plan.identity || !ga->plan.blkcols || ga->d_col_map) return -1;
+  return ga->plan.nblk;
+}
+
+int femb200_bsr_copy(const femb200_assembler *ga, int64_t *blkptr, int32_t *blkcols, double *values) {
+  if (!ga) return FEMB200_ERR_BAD_ARG;
+  if (femb200_bsr_blocks(ga) < 0) return FEMB200_ERR_UNSUPPORTED;
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const LastPlan &pl = ga->plan;
+  if (blkptr) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(blkptr, pl.blkptr, sizeof(int64_t) * (ga->n_nodes + 1), cudaMemcpyDeviceToHost, st));
+  if (blkcols && pl.nblk) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(blkcols, pl.blkcols, sizeof(int32_t) * pl.nblk, cudaMemcpyDeviceToHost, st));
+  if (values && ga->K.nnz) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(values, ga->K.values, sizeof(double) * ga->K.nnz, cudaMemcpyDeviceToHost, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
 int femb200_csr_device(const femb200_assembler *ga, const int64_t **indptr, const int32_t **indices, const double **values) {
   if (!ga) return FEMB200_ERR_BAD_ARG;
   if (indptr) *indptr = ga->K.indptr;
@@ -559,6 +578,17 @@ int femb200_csr_matvec(const femb200_assembler *cga, const double *x, double *y)
   if (!rc) FEMB_CUDA_OK(ctx, cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   dev_free(ctx, dx); dev_free(ctx, dy);
   FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+
+int femb200_add_coo(femb200_assembler *ga, int64_t n, const int64_t *rows, const int64_t *cols, const double *vals) {
+  if (!ga || n < 0 || (n > 0 && (!rows || !cols || !vals))) return FEMB200_ERR_BAD_ARG;
+  for (int64_t k = 0; k < n; ++k)
+    if (rows[k] < 0 || rows[k] >= ga->K.n_rows || cols[k] < 0 || cols[k] >= ga->K.n_rows) return FEMB200_ERR_BAD_ARG;
+  if (n == 0) return 0;
+  FEMB_CUDA_OK(ga->ctx, cudaSetDevice(ga->ctx->device));
+  int rc = csr_add_coo(ga, n, rows, cols, vals);
+  cudaStreamSynchronize(ga->ctx->stream);
   return rc;
 }
 

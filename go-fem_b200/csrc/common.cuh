@@ -225,6 +225,7 @@ int csr_merge_into(femb200_assembler *ga, DeviceCsr *add); // K += add (consumes
 int csr_accumulate_rows(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
                         const double *values);
 int csr_keep_rows(femb200_assembler *ga, const uint8_t *keep);
+int csr_add_coo(femb200_assembler *ga, int64_t n, const int64_t *h_rows, const int64_t *h_cols, const double *h_vals);
 int csr_add_entries(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,
                     const double *values);
 int csr_matvec(femb200_assembler *ga, const double *d_x, double *d_y);

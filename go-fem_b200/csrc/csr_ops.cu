@@ -4,6 +4,8 @@
 //   csr_matvec     : y = K x                   (forces.MulVec(K,u), constitution/solids/patch_test.go:92)
 #include "common.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
+#include <vector>
 
 namespace femb200 {
 
@@ -84,6 +86,45 @@ int csr_merge_into(femb200_assembler *ga, DeviceCsr *add) {
   K = out;
   ga->plan.matches_K = false; // K's pattern is now a union: the cached symbolic plan no longer addresses its slots
   return 0;
+}
+
+// K += triplets (femb200_add_coo; assembler.go:225-231).  The triplets come from the host (a few 12x12 beam blocks in the
+// reference's use): they are ordered by (row, col) with a stable sort, duplicates summed in input order, and the resulting
+// small CSR is merged into K on the device by the same pattern-union kernels repeated AddIsoparametric calls use.
+int csr_add_coo(femb200_assembler *ga, int64_t n, const int64_t *h_rows, const int64_t *h_cols, const double *h_vals) {
+  femb200_ctx *ctx = ga->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t nr = ga->K.n_rows;
+  std::vector<int64_t> perm(n);
+  for (int64_t k = 0; k < n; ++k) perm[k] = k;
+  std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) {
+    return h_rows[a] != h_rows[b] ? h_rows[a] < h_rows[b] : h_cols[a] < h_cols[b];
+  });
+  std::vector<int64_t> indptr(nr + 1, 0);
+  std::vector<int32_t> indices;
+  std::vector<double> values;
+  indices.reserve(n); values.reserve(n);
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t t = perm[k];
+    if (k > 0 && h_rows[perm[k - 1]] == h_rows[t] && h_cols[perm[k - 1]] == h_cols[t]) { values.back() += h_vals[t]; continue; }
+    indices.push_back((int32_t)h_cols[t]);
+    values.push_back(h_vals[t]);
+    indptr[h_rows[t] + 1]++;
+  }
+  for (int64_t r = 0; r < nr; ++r) indptr[r + 1] += indptr[r];
+  DeviceCsr add;
+  add.n_rows = nr;
+  add.nnz = (int64_t)indices.size();
+  int rc;
+  if ((rc = dev_alloc(ctx, &add.indptr, (size_t)nr + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &add.indices, (size_t)add.nnz))) return rc;
+  if ((rc = dev_alloc(ctx, &add.values, (size_t)add.nnz))) return rc;
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(add.indptr, indptr.data(), sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(add.indices, indices.data(), sizeof(int32_t) * add.nnz, cudaMemcpyHostToDevice, st));
+  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(add.values, values.data(), sizeof(double) * add.nnz, cudaMemcpyHostToDevice, st));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st)); // the host vectors die with this frame
+  ga->plan.matches_K = false; // foreign entries: the cached symbolic plan no longer describes K
+  return csr_merge_into(ga, &add);
 }
 
 // ---- multi-GPU pack / unpack ----------------------------------------------------------------------------

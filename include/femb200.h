@@ -130,6 +130,15 @@ int64_t femb200_nnz(const femb200_assembler *ga);
  * summed in ascending element index then call order): indptr[ndof+1] int64, indices[nnz] int32,
  * values[nnz] float64, copied into caller memory.  NULL pointers are skipped. */
 int femb200_csr_copy(const femb200_assembler *ga, int64_t *indptr, int32_t *indices, double *values);
+/* K at node-block granularity (additive API: the 4-byte scalar column indices of femb200_csr_copy are a pure function of
+ * the block pattern, 120 of the 366 MB a config-1 result sends over PCIe).  Valid while K holds exactly ONE
+ * AddIsoparametric call with the identity dof map (else FEMB200_ERR_UNSUPPORTED): n_nodes block rows,
+ * blkptr[n_nodes+1] int64, blkcols[nblk] int32 = column NODE of every block (ascending within a row),
+ * values[nnz] exactly as in femb200_csr_copy.  Scalar row (I, i) of K has the columns mdpn*blkcols[p] + j,
+ * p in [blkptr[I], blkptr[I+1]), j in [0, mdpn), and starts at values[mdpn*mdpn*blkptr[I] + i*mdpn*(blkptr[I+1]-blkptr[I])].
+ * NULL pointers are skipped; femb200_bsr_blocks returns nblk. */
+int64_t femb200_bsr_blocks(const femb200_assembler *ga);
+int femb200_bsr_copy(const femb200_assembler *ga, int64_t *blkptr, int32_t *blkcols, double *values);
 /* The same arrays left on the device (valid until the next add/destroy). */
 int femb200_csr_device(const femb200_assembler *ga, const int64_t **indptr, const int32_t **indices,
                        const double **values);
@@ -138,6 +147,11 @@ int femb200_csr_at(const femb200_assembler *ga, int64_t i, int64_t j, double *ou
 /* K*x on the device, x and y on the host (forces.MulVec(K,u), patch_test.go:92).  (Assemblers with a column map hold
  * global column ids over local rows: femb200_csr_at / _matvec / _slice address K by its own row numbering only.) */
 int femb200_csr_matvec(const femb200_assembler *ga, const double *x, double *y);
+
+/* K += triplets (assembler.go:225-231: AddElement3 writes its 12x12 beam blocks into the same ksolid with
+ * Set(At+v), so models mix isoparametric solids and beams in one K).  rows / cols / vals are n host triplets in any
+ * order, duplicates allowed (summed in input order); the pattern of K grows by the new (row, col) pairs. */
+int femb200_add_coo(femb200_assembler *ga, int64_t n, const int64_t *rows, const int64_t *cols, const double *vals);
 
 /* ---- multi-GPU row-block exchange (one process per GPU; the collective itself is NCCL all-to-all driven by
  * the host layer, these are the device-side pack/unpack steps either side of it) -------------------------

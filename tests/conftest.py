@@ -37,14 +37,18 @@ def meshes(pkg):
     return import_module("gofem_b200.meshes")
 
 
+GO_RAND_SEED1 = (0.6046602879796196, 0.9405090880450124, 0.6645600532184904, 0.4377141871869802,
+                 0.4246374970712657, 0.6868230728671094, 0.0656370192174762, 0.1565192547327912)
+
+
 def go_rand_float64(n):
-    """First n values of Go's math/rand.New(rand.NewSource(1)).Float64() are not reproducible without Go's
-    ALFG table; the patch tests only need *some* interior jitter, so a fixed LCG stands in."""
-    out, s = [], 0x2545F4914F6CDD1D
-    for _ in range(n):
-        s = (s * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-        out.append((s >> 11) / float(1 << 53))
-    return out
+    """The first values of Go's math/rand.New(rand.NewSource(1)).Float64(): the stream patch_test.go:28-40 jitters its
+    interior nodes with.  The eight values the patch tests consume are the ones SURVEY.md section 4 records (Go's additive
+    lagged Fibonacci generator cannot be re-derived without its 607-entry seed table, which is not in the reference tree);
+    asking for more than eight is an error rather than a silent stand-in."""
+    if n > len(GO_RAND_SEED1):
+        raise ValueError("only the first 8 values of Go's seed-1 stream are recorded (SURVEY.md section 4)")
+    return list(GO_RAND_SEED1[:n])
 
 
 # element kind table shared by CPU and GPU tests:

@@ -648,3 +648,85 @@ def test_config1_full_size_properties(pkg, O, meshes):
     rp, ri, rv, ab = og.csr(with_absum=True)
     nerr, rel = compare_csr((ip, ix, v), (rp, ri, rv), ab, TOL)
     print(f"config1 vs oracle: max normalised err {nerr:.2e}, max rel err {rel:.2e}, oracle {og.last_seconds():.1f}s")
+
+
+# ---- additive boundary entries: block-CSR hand-off, foreign triplets ------------------------------------------
+@pytest.mark.parametrize("kind,size", [("tetra4", 4), ("quad4", 7)])
+def test_bsr_copy_reproduces_the_scalar_csr(pkg, meshes, kind, size):
+    """femb200_bsr_copy ships the block pattern (13 MB for config 1) instead of the scalar indices (120 MB): the scalar CSR
+    rebuilt from (blkptr, blkcols) on the host must equal femb200_csr_copy bit for bit."""
+    nodes, conn = meshes.mesh_for(kind, size)
+    if kind == "tetra4":
+        elemT, c, mdpn = pkg.elements.Tetra4(), pkg.solids.Isotropic(200e9, 0.3).Solid3D(), 3
+    else:
+        elemT, c, mdpn = pkg.elements.Quad4(), pkg.solids.Isotropic(200e9, 0.3).Axisymmetric(), 2
+    ra = pkg.RawAssembler(nodes, mdpn)
+    assert ra.add(ra.make_desc(elemT, c), conn=conn) == 0
+    indptr, indices, values = ra.csr()
+    blkptr, blkcols, bvals = ra.bsr()
+    assert np.array_equal(bvals, values)
+    n_nodes = nodes.shape[0]
+    rl = np.diff(blkptr)
+    ip = np.zeros(n_nodes * mdpn + 1, dtype=np.int64)
+    ip[1:] = np.cumsum(np.repeat(rl * mdpn, mdpn))
+    assert np.array_equal(ip, indptr)
+    cols = (blkcols[:, None] * mdpn + np.arange(mdpn)[None, :]).reshape(-1)          # one block row of column ids per block
+    idx = np.concatenate([np.tile(cols[mdpn * blkptr[I]:mdpn * blkptr[I + 1]], mdpn) for I in range(n_nodes)]) if n_nodes else cols
+    assert np.array_equal(idx.astype(np.int32), indices)
+    # a second call merges another pattern into K: the block view is no longer valid and says so
+    assert ra.add(ra.make_desc(elemT, c), conn=conn[: len(conn) // 2]) == 0
+    with pytest.raises(RuntimeError):
+        ra.bsr()
+    ra.close()
+
+
+def test_add_coo_mixes_foreign_triplets_into_k(pkg, meshes):
+    """assembler.go:225-231: AddElement3 adds its beam blocks into the same ksolid.  femb200_add_coo takes such triplets
+    (any order, duplicates, entries outside the solid pattern) and K becomes the pattern union, checked against scipy."""
+    import scipy.sparse as sp
+    nodes, conn = meshes.bcc_tetra4(3)
+    ra = pkg.RawAssembler(nodes, 3)
+    assert ra.add(ra.make_desc(pkg.elements.Tetra4(), pkg.solids.Isotropic(200e9, 0.3).Solid3D()), conn=conn) == 0
+    n = ra.total_dofs()
+    K0 = sp.csr_matrix((ra.csr()[2], ra.csr()[1], ra.csr()[0]), shape=(n, n))
+    rng = np.random.default_rng(5)
+    m = 500
+    rows = rng.integers(0, n, m)
+    cols = rng.integers(0, n, m)
+    rows[:50], cols[:50] = rows[50:100], cols[50:100]                                   # duplicates
+    vals = rng.standard_normal(m) * 1e9
+    assert ra.add_coo(rows, cols, vals) == 0
+    indptr, indices, values = ra.csr()
+    K1 = sp.csr_matrix((values, indices, indptr), shape=(n, n))
+    want = (K0 + sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()).tocsr()
+    assert abs(K1 - want).max() <= 1e-6 * abs(want).max()
+    assert all(np.all(np.diff(indices[indptr[r]:indptr[r + 1]]) > 0) for r in range(0, n, 7))  # canonical: ascending, unique
+    assert K1.nnz >= K0.nnz
+    # the cached plan no longer matches K: numeric-only re-assembly must refuse
+    assert ra.reassemble(ra.make_desc(pkg.elements.Tetra4(), pkg.solids.Isotropic(100e9, 0.3).Solid3D())) != 0
+    # out-of-range triplet
+    assert ra.add_coo([n], [0], [1.0]) != 0
+    # triplets into an EMPTY assembler (beams only)
+    rb = pkg.RawAssembler(nodes, 3)
+    assert rb.add_coo(rows, cols, vals) == 0
+    ip2, ix2, v2 = rb.csr()
+    K2 = sp.csr_matrix((v2, ix2, ip2), shape=(n, n))
+    assert abs(K2 - sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()).max() <= 1e-6 * abs(vals).max()
+    ra.close(); rb.close()
+
+
+def test_keep_rows_then_reassemble_is_refused(pkg, meshes):
+    """after femb200_csr_keep_rows_device the cached plan addresses slots that no longer exist."""
+    import torch
+    nodes, conn = meshes.bcc_tetra4(3)
+    ra = pkg.RawAssembler(nodes, 3)
+    desc = ra.make_desc(pkg.elements.Tetra4(), pkg.solids.Isotropic(200e9, 0.3).Solid3D())
+    assert ra.add(desc, conn=conn) == 0
+    assert ra.reassemble(desc) == 0
+    keep = torch.ones(ra.total_dofs(), dtype=torch.uint8, device="cuda")
+    keep[::2] = 0
+    assert pkg.lib().femb200_csr_keep_rows_device(ra.h, keep.data_ptr()) == 0
+    assert ra.reassemble(desc) != 0
+    with pytest.raises(RuntimeError):
+        ra.bsr()
+    ra.close()
