@@ -89,6 +89,23 @@ def lib():
     L.femb200_kernel_launches.restype = C.c_int64
     L.femb200_sync.argtypes = [vp]
     L.femb200_probe_peaks.argtypes = [vp, C.c_int32, _dp]
+    L.femb200_dist_create.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int64, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.femb200_dist_destroy.argtypes = [vp]
+    L.femb200_dist_add_isoparametric.argtypes = [vp, C.POINTER(ElemDesc)]
+    L.femb200_dist_last_error.argtypes = [vp, _i32p, _i64p, _i32p]
+    L.femb200_dist_assembler.argtypes = [vp]
+    L.femb200_dist_assembler.restype = vp
+    L.femb200_dist_info.argtypes = [vp, _i64p, C.POINTER(C.c_float)]
+    L.femb200_dist_local_nodes.argtypes = [vp, vp, vp]
+    L.femb200_group_create.argtypes = [_i32p, C.c_int32, vp, C.c_int64, C.c_int32, vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.femb200_group_destroy.argtypes = [vp]
+    L.femb200_group_size.argtypes = [vp]
+    L.femb200_group_rank.argtypes = [vp, C.c_int32]
+    L.femb200_group_rank.restype = vp
+    L.femb200_group_add_isoparametric.argtypes = [vp, C.POINTER(ElemDesc), _i32p]
+    L.femb200_mesh_bcc_tetra4.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.POINTER(vp), _i64p, C.POINTER(vp), _i64p]
+    L.femb200_mesh_free.argtypes = [vp, vp]
+    L.femb200_copy_to_host.argtypes = [vp, vp, vp, C.c_int64]
     # host mirror
     L.gofem_elem_info.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _dp, _i32p, _dp, _dp, C.c_char_p, C.c_int]
     L.gofem_elem_basis.argtypes = [C.c_int, _dp, _dp, _dp, _i32p]
@@ -581,3 +598,103 @@ class RawAssembler:
             self.close()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------------------------- multi-GPU (C ABI)
+class DistRank:
+    """femb200_dist: rank `rank` of `world` on the context's device -- device-side partition + owner-computes row block.
+    nodes / conn may be host arrays or device pointers (nodes_ptr / conn_ptr with n_nodes / n_elem)."""
+
+    def __init__(self, ctx, rank, world, mdpn, nn, nodes=None, conn=None, nodes_ptr=None, conn_ptr=None, n_nodes=None, n_elem=None,
+                 conn_is64=False, order_mode=1, handle=None):
+        L = lib()
+        self.ctx, self.mdpn, self.nn, self.owned_handle = ctx, mdpn, nn, handle is None
+        if handle is not None:
+            self.h = handle
+        else:
+            self.h = C.c_void_p()
+            if nodes is not None:
+                nodes = np.ascontiguousarray(nodes, dtype=np.float64).reshape(-1, 3)
+                conn = np.ascontiguousarray(conn)
+                conn_is64 = conn.dtype == np.int64
+                if not conn_is64:
+                    conn = np.ascontiguousarray(conn, dtype=np.int32)
+                self._keep = (nodes, conn)
+                rc = L.femb200_dist_create(ctx, rank, world, nodes.ctypes.data, 0, nodes.shape[0], mdpn, conn.ctypes.data, int(conn_is64), 0,
+                                           conn.size // nn, nn, order_mode, C.byref(self.h))
+            else:
+                rc = L.femb200_dist_create(ctx, rank, world, nodes_ptr, 1, n_nodes, mdpn, conn_ptr, int(conn_is64), 1, n_elem, nn, order_mode, C.byref(self.h))
+            if rc:
+                raise RuntimeError(f"femb200_dist_create -> {rc}")
+
+    def info(self):
+        out = np.zeros(8, dtype=np.int64)
+        ms = C.c_float()
+        lib().femb200_dist_info(self.h, out.ctypes.data_as(_i64p), C.byref(ms))
+        keys = ("local_nodes", "owned_nodes", "local_elems", "chunk_elems", "halo_elems", "nnz", "global_nodes", "global_elems")
+        d = dict(zip(keys, [int(v) for v in out]))
+        d["partition_ms"] = float(ms.value)
+        return d
+
+    def add(self, desc):
+        return lib().femb200_dist_add_isoparametric(self.h, C.byref(desc))
+
+    def last_error(self):
+        k, e, q = C.c_int32(), C.c_int64(), C.c_int32()
+        lib().femb200_dist_last_error(self.h, C.byref(k), C.byref(e), C.byref(q))
+        return k.value, e.value, q.value
+
+    def assembler(self):
+        return lib().femb200_dist_assembler(self.h)
+
+    def local_nodes(self):
+        n = self.info()["local_nodes"]
+        l2g, owned = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.uint8)
+        lib().femb200_dist_local_nodes(self.h, l2g.ctypes.data, owned.ctypes.data)
+        return l2g, owned
+
+    def row_block(self):
+        """(global scalar rows ascending, indptr, indices (global), values) of the rows this rank owns -- host copy, tests only."""
+        L = lib()
+        ga = self.assembler()
+        n, nnz = L.femb200_total_dofs(ga), L.femb200_nnz(ga)
+        indptr = np.zeros(n + 1, dtype=np.int64)
+        indices = np.zeros(nnz, dtype=np.int32)
+        values = np.zeros(nnz, dtype=np.float64)
+        rc = L.femb200_csr_copy(ga, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data)
+        if rc:
+            raise RuntimeError(f"femb200_csr_copy -> {rc}")
+        l2g, owned = self.local_nodes()
+        m = self.mdpn
+        lrows = (np.nonzero(owned)[0][:, None] * m + np.arange(m)[None, :]).ravel()
+        grows = (l2g[np.nonzero(owned)[0]].astype(np.int64)[:, None] * m + np.arange(m)[None, :]).ravel()
+        lens = indptr[lrows + 1] - indptr[lrows]
+        ptr = np.zeros(lrows.size + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        take = np.concatenate([np.arange(indptr[r], indptr[r + 1]) for r in lrows]) if lrows.size else np.zeros(0, dtype=np.int64)
+        # rows of nodes this rank does not own must be empty
+        other = np.ones(n, dtype=bool)
+        other[lrows] = False
+        assert np.all((indptr[1:] - indptr[:-1])[other] == 0), "a non-owned row holds entries"
+        return grows, ptr, indices[take], values[take]
+
+    def close(self):
+        if self.h and self.owned_handle:
+            lib().femb200_dist_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_mesh_bcc_tetra4(ctx, nx, ny, nz, h, jittered=True):
+    """femb200_mesh_bcc_tetra4 -> (nodes device pointer, n_nodes, conn device pointer (int32), n_elem); free with lib().femb200_mesh_free."""
+    dn, dc = C.c_void_p(), C.c_void_p()
+    nn_, ne = C.c_int64(), C.c_int64()
+    rc = lib().femb200_mesh_bcc_tetra4(ctx, nx, ny, nz, float(h), int(jittered), C.byref(dn), C.byref(nn_), C.byref(dc), C.byref(ne))
+    if rc:
+        raise RuntimeError(f"femb200_mesh_bcc_tetra4 -> {rc}")
+    return dn.value, nn_.value, dc.value, ne.value

@@ -18,7 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
            "-Xptxas", "-v", "-DFEMB200_BUILD"]
-CU_SOURCES = ["api.cu", "symbolic.cu", "numeric.cu", "srows.cu", "csr_ops.cu"]
+CU_SOURCES = ["api.cu", "symbolic.cu", "numeric.cu", "srows.cu", "csr_ops.cu", "dist.cu", "mesh.cu"]
 CXX_SOURCES = ["host_capi.cpp"]
 
 
@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
             print(o)
     objs = [os.path.join(OBJ, s + ".o") for s in CU_SOURCES]
     objs += [os.path.join(OBJ, s + ".o") for s in CXX_SOURCES if os.path.exists(os.path.join(HOST, s))]
-    _run([NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static"], os.path.join(OBJ, "link.log"))
+    _run([NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static", "-lpthread"], os.path.join(OBJ, "link.log"))
     return OUT
 
 

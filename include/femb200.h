@@ -188,6 +188,51 @@ int femb200_csr_add_entries_async(femb200_assembler *ga, int64_t n_rows, const i
  * does not own, a rank keeps exactly its row block of the distributed K. */
 int femb200_csr_keep_rows_device(femb200_assembler *ga, const uint8_t *keep);
 
+/* ---- multi-GPU behind the C ABI: device-side partition, owner-computes row blocks --------------------------
+ * The reference has ONE assembler and ONE call (assembler.go:21-31, assembler_isoparametric.go:28).  A femb200_dist is rank
+ * `rank` of `world` (one process per GPU; or one host thread per GPU inside a femb200_group): it receives the WHOLE mesh,
+ * partitions it on its device -- element order (0 = as given, 1 = Morton order of the element centroids, 21 bits per axis),
+ * contiguous chunks of equal element count, a node (row block) belongs to the lowest rank touching it -- and assembles the
+ * rows it owns from every element that touches them (its chunk's plus the halo of the other chunks), in ascending global
+ * element index: the row block is bit-identical to the same rows of a single-GPU K, and no data-path collective exists.
+ * K of femb200_dist_assembler(): rows = local nodes (femb200_dist_local_nodes gives their global ids and which are owned,
+ * rows of non-owned nodes are empty), column indices = GLOBAL dof ids. */
+typedef struct femb200_dist femb200_dist;
+int femb200_dist_create(femb200_ctx *ctx, int32_t rank, int32_t world, const double *nodes, int32_t nodes_on_device, int64_t n_nodes,
+                        int32_t model_dofs_per_node, const void *conn, int32_t conn_is_int64, int32_t conn_on_device, int64_t n_elem,
+                        int32_t nn, int32_t order_mode, femb200_dist **out);
+void femb200_dist_destroy(femb200_dist *d);
+/* (*GeneralAssembler).AddIsoparametric for this rank's row block; same error semantics (femb200_dist_last_error reports the
+ * lowest failing element of THIS rank in global numbering; the lowest over all ranks is what the reference would report). */
+int femb200_dist_add_isoparametric(femb200_dist *d, const femb200_elem_desc *desc);
+int femb200_dist_last_error(const femb200_dist *d, int32_t *kind, int64_t *elem, int32_t *qp);
+femb200_assembler *femb200_dist_assembler(femb200_dist *d);
+/* out = { local nodes, owned nodes, local elements (own + halo), elements of the rank's chunk, halo elements, nnz of the row
+ * block, global nodes, global elements }; *partition_ms = device time of the partition (CUDA events). */
+int femb200_dist_info(const femb200_dist *d, int64_t out[8], float *partition_ms);
+int femb200_dist_local_nodes(const femb200_dist *d, int32_t *node_l2g /* [local nodes] */, uint8_t *owned /* [local nodes] */);
+/* One process, several devices -- what a cgo caller uses: a context, a femb200_dist and a host thread per
+ * device; nodes / conn are host arrays (a Go []r3.Vec and flattened []int). */
+typedef struct femb200_group femb200_group;
+int femb200_group_create(const int32_t *devices, int32_t ndev, const double *nodes, int64_t n_nodes, int32_t model_dofs_per_node,
+                         const void *conn, int32_t conn_is_int64, int64_t n_elem, int32_t nn, int32_t order_mode, femb200_group **out);
+void femb200_group_destroy(femb200_group *g);
+int32_t femb200_group_size(const femb200_group *g);
+femb200_dist *femb200_group_rank(femb200_group *g, int32_t rank);
+/* AddIsoparametric on every device at once; on an element error returns the status of the rank holding the lowest failing
+ * element (what the sequential reference loop reports, fem.go:140) and stores that rank in *rank_out (-1 when all succeeded). */
+int femb200_group_add_isoparametric(femb200_group *g, const femb200_elem_desc *desc, int32_t *rank_out);
+
+/* Synthetic meshes generated on the device (benchmarks and tests only; no reference counterpart): the BCC tetrahedral mesh
+ * of an nx x ny x nz cell box, node for node and element for element what go-fem_b200/meshes.py bcc_tetra4_box builds on the
+ * host (benchmark_test.go:34-35 uses manigold's BCC mesher: only its counts are pinned).  Arrays are allocated by the library
+ * (device memory) and released with femb200_mesh_free. */
+int femb200_mesh_bcc_tetra4(femb200_ctx *ctx, int32_t nx, int32_t ny, int32_t nz, double h, int32_t jittered, double **d_nodes,
+                            int64_t *n_nodes, int32_t **d_conn, int64_t *n_elem);
+void femb200_mesh_free(femb200_ctx *ctx, void *device_ptr);
+/* Copies `bytes` of a device array of this library (a generated mesh, a CSR array of femb200_csr_device) into host memory. */
+int femb200_copy_to_host(femb200_ctx *ctx, void *host_dst, const void *device_src, int64_t bytes);
+
 /* Element -> CSR slot map of the last add call (north_star subsystem 1):
  * slot[e][a][b] = index into the node-block CSR of block (node a of e, node b of e); the scalar entry
  * of dof pair (i,j) sits at values[indptr[mdpn*node_a+dofmap[i]] + pos*nu + j'].  Copied to the host. */
