@@ -142,17 +142,6 @@ def make_workload(name, size):
                 desc=desc.format(s=s, ne=conn.shape[0], nd=nodes.shape[0] * ndn), size=s, name=name)
 
 
-def algorithmic_bytes(w, nnz):
-    """Per-launch algorithmic bytes of the dominant kernel k_rows: staged geometry records
-    (one per element and quadrature point) + incidence list (n2e_t) + element->slot map (pos16) read, CSR values
-    written.  Record = 4 doubles per node when a node carries 3 values (f rides in the 4th), else nn*NV + f padded even."""
-    ne, nn = w["conn"].shape
-    nv = {"tetra4": 3, "hexa8": 3, "tetra10": 3, "hexa20": 3, "quad4": 3}[w["name"]]
-    nqp = len(w["elemT"].Quadrature()[1])
-    rec = 4 * nn if nv == 3 else ((nn * nv + 2) & ~1)
-    return 8 * rec * nqp * ne + 4 * nn * ne + 2 * nn * nn * ne + 8 * nnz
-
-
 def compulsory_bytes(w, nnz, ndof):
     """SURVEY section 8(d) B_alg of one full call: int32 connectivity + node coordinates in, CSR (indptr int64 + indices int32 +
     values f64) out."""
@@ -183,20 +172,20 @@ def run_reference(args):
     if args.size:
         size = args.size
     elif name == "tetra4":
-        # bounded sample: about 90 s of CPU work for the whole run at ~1.1e5 elements/s (single thread), never more than the
-        # workload itself; BCC cube N -> 12 N^2 (N-1) elements
-        budget = 90.0 / max(1, args.steps + args.warmup) * 1.1e5
-        size = 8
-        while size < 48 and 12 * (size + 1) ** 2 * size <= budget:
-            size += 1
+        # the FULL config-1 mesh every step (12.4 s per step on one core: 25 steps fit the driver's limit); a smaller sample only
+        # when the requested step count would run past ~25 minutes
+        size = 48
+        while size > 8 and 12 * size * size * (size - 1) / 1.05e5 * (args.steps + min(args.warmup, 1)) > 1500.0:
+            size -= 4
     else:
         size = {"quad4": 700, "hexa8": 40, "tetra10": 16, "hexa20": 12}[name]
     w = make_workload(name, size)
     full = make_workload_desc(name, args.size)
     times = []
-    for i in range(args.warmup + args.steps):
+    nwarm = min(args.warmup, 1)          # a CPU loop has nothing to warm beyond the page cache: one untimed pass
+    for i in range(nwarm + args.steps):
         dt = cpu_port_seconds(w, w["nodes"], w["conn"])
-        if i >= args.warmup:
+        if i >= nwarm:
             times.append(dt)
     ne = w["conn"].shape[0]
     v = ne * len(times) / sum(times)
@@ -204,7 +193,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "K assembly elements/s", "value": v, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": full, "sample": w["desc"]},
+            "config": {"workload": full, "sample": w["desc"], "same_config": w["desc"] == full},
             "cpu_baseline": {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
                              "sample": f"{w['desc']} ({ne} elements per step); C port of the reference algorithm incl. full COO + sort-accumulate; go toolchain: "
                                        + ("present but modules unavailable offline" if go_probe.returncode == 0 else "absent")},
@@ -221,212 +210,194 @@ def make_workload_desc(name, size):
     return desc.format(s=s, ne="?", nd="?")
 
 
+def dense_flops_per_element(d, nn, ndn, nqp, dimC, radial):
+    """SURVEY 8(d) F_alg: dense-formulation flops of the reference arithmetic per element."""
+    nd = nn * ndn
+    per_qp = 2 * d * d * nn + (2.0 / 3.0 * d ** 3 + 2 * d * d * nn) + 2 * nd * dimC ** 2 + 2 * nd * nd * dimC + 2 * nd * nd
+    if radial:
+        per_qp += 2 * nn + 1
+    return nqp * per_qp
+
+
+def s_mesh_strong_scaling(pkg, ctx, desc, rank, world, dev, steps=3):
+    """The scaling mesh of SURVEY 8(d): Tetra4 BCC N=204, 101,376,576 elements / 51.3 M dofs, generated on the device,
+    partitioned on the device (Morton order) and assembled by `world` ranks (strong scaling: total work fixed)."""
+    import ctypes as C
+    import torch
+    L = pkg.lib()
+    N = int(os.environ.get("FEMB200_BENCH_S_SIZE", "204"))
+    t0 = time.perf_counter()
+    dn, n_nodes, dc, n_elem = pkg.device_mesh_bcc_tetra4(ctx, N, N, N, 1.0 / N)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    d = pkg.DistRank(ctx, rank, world, 3, 4, nodes_ptr=dn, conn_ptr=dc, n_nodes=n_nodes, n_elem=n_elem, order_mode=1)
+    part_wall = time.perf_counter() - t0
+    info = d.info()
+    L.femb200_mesh_free(ctx, dc)            # the partition keeps only the rank's share
+    ms = []
+    for i in range(steps + 1):
+        d.reset()
+        rc = d.add(desc)
+        if rc:
+            raise RuntimeError(f"S mesh: femb200_dist_add_isoparametric -> {rc} {d.last_error()}")
+        ph = (C.c_float * pkg.N_TIMERS)()
+        L.femb200_phase_ms(d.assembler(), ph)
+        if i > 0:
+            ms.append(float(ph[6]))
+    nnz = d.info()["nnz"]
+    d.close()
+    L.femb200_mesh_free(ctx, dn)
+    return {"n_elem": n_elem, "n_dofs": 3 * n_nodes, "ms": float(np.mean(ms)), "nnz_rank": nnz, "partition_ms_device": info["partition_ms"],
+            "partition_s_wall": part_wall, "mesh_generation_s": gen_s, "local_elems": info["local_elems"], "halo_elems": info["halo_elems"],
+            "chunk_elems": info["chunk_elems"]}
+
+
 def run_multi_gpu(args, rank, world, local_rank):
-    """N > 1: weak scaling.  Global mesh = BCC box of (48*N) x 48 x 48 cells (N x config 1); elements in cell-major
-    (space-filling) order are split into N contiguous chunks, one per GPU; a node (row block) belongs to the lowest
-    rank touching it.  A step = local assembly of the chunk (symbolic + numeric, inputs resident in HBM) + the
-    exchange that leaves every GPU owning its row block of the distributed CSR K:
-      exchange (headline, the north star's scheme): owned rows assembled from [own elements ; halo elements (pattern
-        only)], interface rows assembled from the own elements touching foreign nodes, packed per owner, ONE NCCL
-        all-to-all over NVLink (sizes fixed by the partition plan), added in place in ascending source rank;
-      owner_computes (reported alongside): halo elements are assembled numerically by the owner as well -- redundant
-        O(surface) work, no collective at all, rows bit-identical to the single-GPU result.
-    Timed with CUDA events on the single stream everything runs on, max over ranks."""
+    """N > 1, one process per GPU, everything through the C ABI (femb200_dist_*): weak scaling on a CUBE-shaped BCC Tetra4 mesh
+    with N_side = round(48 * N^(1/3)) (elements per GPU = config 1 within 2 %), generated on the device, partitioned on the
+    device in Morton order; a node (row block) belongs to the lowest rank touching it and every rank assembles the rows it
+    owns from all elements touching them (own chunk + halo), ascending global element index: no data-path collective, rows
+    bit-identical to one GPU (tests/test_dist_gpu.py).  A step = femb200_dist_reset + femb200_dist_add_isoparametric (fresh
+    assembler + AddIsoparametric, like the reference benchmark); CUDA events on the library stream, max over ranks.
+    Also in the line: the partition time, a host-buffer e2e (mesh in from pinned memory incl. the partition, the rank's CSR row
+    block out) and the strong-scaling point of the 101 M-element mesh."""
     import ctypes as C
     import torch
     import torch.distributed as dist
-    from importlib import import_module
     pkg = entry.load_package()
-    D = import_module("gofem_b200.distributed")
-    M = import_module("gofem_b200.meshes")
-    dev = torch.device("cuda", local_rank)
-    N = args.size or 48
-    nodes, conn = M.bcc_tetra4_box(N * world, N, N, 1.0 / N)
-    ne_total = conn.shape[0]
-    bounds = D.chunk_bounds(ne_total, world)
-    plan = D.ExchangePlan(nodes.shape[0], conn, bounds, rank, 3)
-    iplan = D.InterfacePlan(plan, nodes.shape[0], conn, bounds, 3, dist)
-    # rank-local node numbering (own + ghost nodes, ascending global id): every device array of a step is sized by
-    # the rank's share of the mesh; K rows are local, K column indices global
-    gids = np.sort(np.concatenate([np.arange(bounds[rank], bounds[rank + 1]), plan.halo_elems]))
-    ln = D.LocalNumbering(nodes, conn[gids])
-    lconn, nhalo = plan.local_connectivity(conn, bounds)            # [own ; halo] for the row-exchange variant
-    my = ln.conn(lconn)
-    own_conn = conn[bounds[rank]:bounds[rank + 1]]
-    out_conn = ln.conn(own_conn[plan.send_elems]) if plan.send_elems.size else np.zeros((0, 4), dtype=np.int32)
-    ghost = ln.conn(conn[gids])                                     # own + halo in ascending GLOBAL element index
-    n_local = ln.nodes.shape[0]
-    d_nodes = torch.from_numpy(ln.nodes).to(dev)
-    d_l2g = torch.from_numpy(ln.l2g.astype(np.int32)).to(dev)
-    d_conn = torch.from_numpy(my).to(dev)
-    d_ghost = torch.from_numpy(ghost).to(dev)
-    d_out = torch.from_numpy(out_conn).to(dev) if out_conn.size else torch.zeros(4, dtype=torch.int32, device=dev)
-    m_own = torch.as_tensor(ln.node_mask(plan.own_node_mask), device=dev)
-    m_send = torch.as_tensor(ln.node_mask(plan.send_node_mask), device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    elemT, c = pkg.elements.Tetra4(), pkg.solids.Isotropic(E_MOD, NU).Solid3D()
-    # two library contexts per rank, one stream and one host thread each: the owned row block and the (small) set of
-    # outgoing interface rows are assembled concurrently, the second call filling the gaps of the first
-    from concurrent.futures import ThreadPoolExecutor
-    holder = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=n_local)
-    holder_b = pkg.RawAssembler(None, 3, device=local_rank, nodes_device_ptr=d_nodes.data_ptr(), n_nodes=n_local)
     L = pkg.lib()
-    s0 = torch.cuda.current_stream()
-    sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    L.femb200_ctx_set_stream(holder.ctx, C.c_void_p(sa.cuda_stream))
-    L.femb200_ctx_set_stream(holder_b.ctx, C.c_void_p(sb.cuda_stream))
-    L.femb200_ctx_set_concurrent(holder.ctx, 1)
-    L.femb200_ctx_set_concurrent(holder_b.ctx, 1)
-    pool = ThreadPoolExecutor(max_workers=1)
-    desc = holder.make_desc(elemT, c)
-    px = D.PlannedExchange(iplan, dev, local=ln)
-
-    class View:
-        def __init__(self, h):
-            self.h = h
-
-        def csr_device(self):
-            return tuple(v.value for v in _csr_dev(L, self.h))
-
-        def total_dofs(self):
-            return L.femb200_total_dofs(self.h)
-
-        def nnz(self):
-            return L.femb200_nnz(self.h)
-
-    def new_assembler(mask, ctx=None):
-        h = C.c_void_p()
-        assert L.femb200_assembler_create(ctx or holder.ctx, C.c_void_p(d_nodes.data_ptr()), n_local, 3, 1, C.byref(h)) == 0
-        L.femb200_assembler_set_node_mask_device(h, C.c_void_p(mask.data_ptr()))
-        assert L.femb200_assembler_set_column_map_device(h, C.c_void_p(d_l2g.data_ptr()), nodes.shape[0]) == 0
-        return h
-
-    def assemble_outgoing():
-        # interface rows to send: own elements touching foreign nodes, rows of foreign nodes only
-        torch.cuda.set_device(local_rank)
-        hb = new_assembler(m_send, holder_b.ctx)
-        rc = L.femb200_add_isoparametric(hb, C.byref(desc), C.c_void_p(d_out.data_ptr()), 0, 1, out_conn.shape[0])
-        assert rc == 0, rc
-        return hb
-
-    sub_t = {}
-
-    def step_exchange_diag():
-        """FEMB200_BENCH_SUBSTEPS=1: the same step serialised, host clock per sub-step (diagnostics only)."""
-        def mark(name, t0):
-            torch.cuda.synchronize()
-            sub_t[name] = sub_t.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
-            return time.perf_counter()
-        t0 = time.perf_counter()
-        ha = new_assembler(m_own)
-        rc = L.femb200_add_isoparametric_halo(ha, C.byref(desc), C.c_void_p(d_conn.data_ptr()), 0, 1, my.shape[0], nhalo)
-        t0 = mark("owned_block", t0)
-        hb = assemble_outgoing()
-        t0 = mark("outgoing_rows", t0)
-        be_a, be_b = D.Femb200Backend(pkg, View(ha), dev), D.Femb200Backend(pkg, View(hb), dev)
-        tt = [t0]
-
-        def ap():
-            s0.wait_stream(sb)
-            tt[0] = mark("pack", tt[0])
-
-        def ac():
-            tt[0] = mark("all_to_all", tt[0])
-            sa.wait_stream(s0)
-        sent = px.run(be_a, be_b, dist, after_pack=ap, after_collective=ac)
-        s0.wait_stream(sa)
-        t0 = mark("add", tt[0])
-        nnz = L.femb200_nnz(ha)
-        L.femb200_assembler_destroy(ha)
-        L.femb200_assembler_destroy(hb)
-        mark("destroy", t0)
-        return sent, nnz
-
-    def step_exchange():
-        if os.environ.get("FEMB200_BENCH_SUBSTEPS"):
-            return step_exchange_diag()
-        fut = pool.submit(assemble_outgoing)
-        # owned row block: own elements + pattern-only halo, rows of owned nodes only
-        ha = new_assembler(m_own)
-        rc = L.femb200_add_isoparametric_halo(ha, C.byref(desc), C.c_void_p(d_conn.data_ptr()), 0, 1, my.shape[0], nhalo)
-        assert rc == 0, rc
-        hb = fut.result()
-        # both calls have synchronised their streams; pack on sb -> all-to-all on s0 -> adds on sa -> s0 waits for sa
-        sent = px.run(D.Femb200Backend(pkg, View(ha), dev), D.Femb200Backend(pkg, View(hb), dev), dist,
-                      after_pack=lambda: s0.wait_stream(sb), after_collective=lambda: sa.wait_stream(s0))
-        s0.wait_stream(sa)
-        nnz = L.femb200_nnz(ha)
-        L.femb200_assembler_destroy(ha)      # synchronises its stream: the exchange is complete when the step returns
-        L.femb200_assembler_destroy(hb)
-        return sent, nnz
-
-    def step_owner_computes():
-        ha = new_assembler(m_own)
-        rc = L.femb200_add_isoparametric(ha, C.byref(desc), C.c_void_p(d_ghost.data_ptr()), 0, 1, ghost.shape[0])
-        assert rc == 0, rc
-        nnz = L.femb200_nnz(ha)
-        L.femb200_assembler_destroy(ha)
-        return 0, nnz
-
+    dev = torch.device("cuda", local_rank)
+    base = args.size or 48
+    N = int(round(base * world ** (1.0 / 3.0)))
+    holder = pkg.RawAssembler(np.zeros((1, 3)), 3, device=local_rank)
+    ctx = holder.ctx
+    dn, n_nodes, dc, n_elem = pkg.device_mesh_bcc_tetra4(ctx, N, N, N, 1.0 / N)
+    t0 = time.perf_counter()
+    d = pkg.DistRank(ctx, rank, world, 3, 4, nodes_ptr=dn, conn_ptr=dc, n_nodes=n_nodes, n_elem=n_elem, order_mode=1)
+    part_wall = time.perf_counter() - t0
+    info = d.info()
+    desc = holder.make_desc(pkg.elements.Tetra4(), pkg.solids.Isotropic(E_MOD, NU).Solid3D())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     warmup = max(args.warmup, 3)
 
-    def timed(step):
-        for _ in range(warmup):
-            step()
-            flush.fill_(1)
+    def step():
+        d.reset()
+        rc = d.add(desc)
+        if rc:
+            raise RuntimeError(f"femb200_dist_add_isoparametric -> {rc} {d.last_error()}")
+        ph = (C.c_float * pkg.N_TIMERS)()
+        L.femb200_phase_ms(d.assembler(), ph)
+        return [float(x) for x in ph]
+
+    for _ in range(warmup):
+        step()
+        flush.fill_(1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.femb200_kernel_launches(ctx)
+    phases = []
+    for _ in range(args.steps):
+        flush.fill_(1)
         torch.cuda.synchronize()
         dist.barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        launches0 = L.femb200_kernel_launches(holder.ctx)
-        times = []
-        sent = nnz = 0
-        sub_t.clear()
-        for _ in range(args.steps):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            dist.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            sent, nnz = step()
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        launches = L.femb200_kernel_launches(holder.ctx) - launches0
-        clocks = sampler.finish()
-        t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot = torch.tensor([float(sent), float(nnz)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tot)
-        return float(t.item()), tot[0].item(), tot[1].item(), int(launches), clocks
+        phases.append(step())
+    torch.cuda.synchronize()
+    launches = L.femb200_kernel_launches(ctx) - launches0
+    clocks = sampler.finish()
+    ph_mean = np.mean(np.array(phases), axis=0)
+    t = torch.tensor([float(ph_mean[6])], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    nnz_rank = d.info()["nnz"]
+    stats = torch.tensor([float(nnz_rank), float(info["halo_elems"]), float(info["local_elems"]), float(info["partition_ms"])], dtype=torch.float64, device=dev)
+    tot = stats.clone()
+    dist.all_reduce(tot)
+    mx = stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
 
-    ms_x, sent_b, nnz_x, launches_x, _ = timed(step_exchange)
-    sub_x = dict(sub_t)
-    mism = torch.tensor([float(px.mismatches())], dtype=torch.float64, device=dev)
-    dist.all_reduce(mism)
-    ms, _, nnz_t, launches, clocks = timed(step_owner_computes)
-    halo_tot = torch.tensor([float(nhalo)], dtype=torch.float64, device=dev)
-    dist.all_reduce(halo_tot)
+    # ---- end to end with host buffers: the whole mesh in (every rank partitions it itself), the rank's row block out ------
+    h_nodes = torch.empty(n_nodes * 3, dtype=torch.float64).pin_memory()
+    h_conn = torch.empty(n_elem * 4, dtype=torch.int32).pin_memory()
+    L.femb200_copy_to_host(ctx, h_nodes.data_ptr(), dn, h_nodes.numel() * 8)
+    L.femb200_copy_to_host(ctx, h_conn.data_ptr(), dc, h_conn.numel() * 4)
+    n_local_dofs = info["local_nodes"] * 3
+    h_indptr = torch.empty(n_local_dofs + 1, dtype=torch.int64).pin_memory()
+    h_indices = torch.empty(nnz_rank, dtype=torch.int32).pin_memory()
+    h_values = torch.empty(nnz_rank, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        h = C.c_void_p()
+        rc = L.femb200_dist_create(ctx, rank, world, h_nodes.data_ptr(), 0, n_nodes, 3, h_conn.data_ptr(), 0, 0, n_elem, 4, 1, C.byref(h))
+        assert rc == 0, rc
+        rc = L.femb200_dist_add_isoparametric(h, C.byref(desc))
+        assert rc == 0, rc
+        rc = L.femb200_csr_copy(L.femb200_dist_assembler(h), h_indptr.data_ptr(), h_indices.data_ptr(), h_values.data_ptr())
+        assert rc == 0, rc
+        L.femb200_dist_destroy(h)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_t = []
+    for _ in range(e2e_steps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_t.append(time.perf_counter() - t0)
+    te = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    bytes_io = torch.tensor([float(h_nodes.numel() * 8 + h_conn.numel() * 4), float(h_indptr.numel() * 8 + h_indices.numel() * 4 + h_values.numel() * 8)],
+                            dtype=torch.float64, device=dev)
+    dist.all_reduce(bytes_io)
+    d.close()
+    L.femb200_mesh_free(ctx, dn)
+    L.femb200_mesh_free(ctx, dc)
+    del flush, h_nodes, h_conn, h_indptr, h_indices, h_values
+    torch.cuda.empty_cache()
+
+    # ---- strong scaling on the 101 M-element mesh -----------------------------------------------------------------------------
+    s_line = None
+    if os.environ.get("FEMB200_BENCH_S", "1") != "0":
+        sres = s_mesh_strong_scaling(pkg, ctx, desc, rank, world, dev)
+        ts = torch.tensor([sres["ms"], sres["partition_ms_device"], float(sres["halo_elems"]), float(sres["nnz_rank"])], dtype=torch.float64, device=dev)
+        tmax = ts.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = ts.clone()
+        dist.all_reduce(tsum)
+        s_line = {"workload": f"Tetra4 BCC N=204: {sres['n_elem']} elements / {sres['n_dofs']} dofs over {world} GPUs (total work fixed)",
+                  "value": sres["n_elem"] / (tmax[0].item() * 1e-3), "unit": "elements/s", "ms_per_step": tmax[0].item(),
+                  "partition_ms_device_max": tmax[1].item(), "mesh_generation_s_rank0": sres["mesh_generation_s"],
+                  "halo_elements_total": tsum[2].item(), "nnz_total": tsum[3].item(), "steps": 3}
+
     if rank == 0:
-        value = ne_total / (ms * 1e-3)
+        value = n_elem / (ms * 1e-3)
+        e2e_value = n_elem / float(te.item())
+        names = list(pkg.TIMER_NAMES)
         line = {"metric": "K assembly elements/s", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"Tetra4 BCC box {N * world}x{N}x{N}: {ne_total} elements / {nodes.shape[0] * 3} dofs ({world} x config 1), Isotropic(E=200e9, nu=0.3).Solid3D",
-                           "l2": "flushed between timed steps (256 MiB write)", "inputs": "nodes f64 + int32 connectivity chunk resident in HBM",
-                           "multi_gpu": "contiguous cell-major element chunks, one per GPU; a node (row block) belongs to the lowest rank touching it; "
-                                        "owner computes: every rank assembles its own elements plus the halo elements touching its rows "
-                                        "(redundant O(surface) work, ascending global element order => rows bit-identical to 1 GPU), no data-path collective; "
-                                        "the NCCL row exchange of partial interface rows is timed alongside (key 'row_exchange')"},
-                "dofs_per_s": value * nodes.shape[0] * 3 / ne_total, "nnz_total": nnz_t, "redundant_halo_elements_total": halo_tot.item(),
-                "row_exchange": {"value": ne_total / (ms_x * 1e-3), "unit": "elements/s", "ms_per_step": ms_x, "gpu_launches": launches_x,
-                                 "interface_bytes_sent_total": sent_b, "nnz_total": nnz_x, "plan_mismatches": mism.item(),
-                                 "note": "north-star scheme: owned rows from [own ; halo (pattern only)], interface rows from the own elements touching foreign "
-                                         "nodes (second context, concurrent), ONE NCCL all-to-all with plan-time sizes, in-place add in ascending source rank"},
-                "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                        "note": "multi-GPU result stays distributed on the devices (row blocks); host-buffer e2e is reported at N=1"},
-                "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None}
-        if sub_x:
-            line["row_exchange"]["substeps_ms_rank0_serialised"] = {k: v / args.steps for k, v in sub_x.items()}
+                "config": {"workload": f"Tetra4 BCC cube N={N}: {n_elem} elements / {3 * n_nodes} dofs ({n_elem / 1299456:.2f} x config 1 on {world} GPUs), "
+                                       "Isotropic(E=200e9, nu=0.3).Solid3D",
+                           "l2": "flushed between timed steps (256 MiB write)", "inputs": "mesh generated on the device; the rank's share resident in HBM",
+                           "multi_gpu": "C ABI femb200_dist_*: Morton order of element centroids -> contiguous chunks; a node (row block) belongs to the lowest "
+                                        "rank touching it; every rank assembles its rows from own + halo elements in ascending global element index "
+                                        "(bit-identical to one GPU); NO data-path collective (the path shards into independent rows; the north star's "
+                                        "NCCL reduce-scatter variant measured 60-68 % efficiency in round 1, see DESIGN.md section 7)"},
+                "dofs_per_s": value * 3 * n_nodes / n_elem, "nnz_total": tot[0].item(),
+                "redundant_halo_elements_total": tot[1].item(), "local_elements_max": mx[2].item(),
+                "partition": {"ms_device_max": mx[3].item(), "s_wall_rank0": part_wall, "where": "on the device, every rank over the whole mesh (no communication)"},
+                "phases_ms_rank0": dict(zip(names, [float(x) for x in ph_mean])),
+                "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": bytes_io[0].item(), "d2h_bytes_per_step": bytes_io[1].item(),
+                        "ms_per_step": 1e3 * float(te.item()),
+                        "note": "per rank: whole mesh in from pinned host memory (nodes f64 + int32 connectivity), partition + assembly, the rank's CSR row block "
+                                "(indptr int64, global indices int32, values f64) out to pinned host memory; host clock, max over ranks; bytes summed over ranks"},
+                "strong_scaling_S": s_line,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
@@ -556,38 +527,48 @@ def main():
     # ---- end to end through the host API with host buffers ------------------------------------------
     h_nodes = torch.from_numpy(nodes).pin_memory()
     h_conn = torch.from_numpy(conn).pin_memory()          # int64: a Go []int
+    nblk = nnz // (w["ndn"] * w["ndn"])
+    h_blkptr = torch.empty(nodes.shape[0] + 1, dtype=torch.int64).pin_memory()
+    h_blkcols = torch.empty(nblk, dtype=torch.int32).pin_memory()
+    h_values = torch.empty(nnz, dtype=torch.float64).pin_memory()
     h_indptr = torch.empty(ndof + 1, dtype=torch.int64).pin_memory()
     h_indices = torch.empty(nnz, dtype=torch.int32).pin_memory()
-    h_values = torch.empty(nnz, dtype=torch.float64).pin_memory()
 
-    def e2e_step():
+    def e2e_step(block):
+        # block=True: K leaves as node-block pattern + values (femb200_bsr_copy: the scalar column indices are a pure function
+        # of the block pattern and stay on the device); block=False: the scalar CSR of femb200_csr_copy
         h = C.c_void_p()
         rc = L.femb200_assembler_create(ctx_holder.ctx, C.c_void_p(h_nodes.data_ptr()), nodes.shape[0], w["ndn"], 0, C.byref(h))
         assert rc == 0
         rc = L.femb200_add_isoparametric(h, C.byref(desc0), C.c_void_p(h_conn.data_ptr()), 1, 0, ne)
         assert rc == 0, rc
-        rc = L.femb200_csr_copy(h, C.c_void_p(h_indptr.data_ptr()), C.c_void_p(h_indices.data_ptr()), C.c_void_p(h_values.data_ptr()))
-        assert rc == 0
+        if block:
+            rc = L.femb200_bsr_copy(h, C.c_void_p(h_blkptr.data_ptr()), C.c_void_p(h_blkcols.data_ptr()), C.c_void_p(h_values.data_ptr()))
+        else:
+            rc = L.femb200_csr_copy(h, C.c_void_p(h_indptr.data_ptr()), C.c_void_p(h_indices.data_ptr()), C.c_void_p(h_values.data_ptr()))
+        assert rc == 0, rc
         L.femb200_assembler_destroy(h)
 
-    for _ in range(warmup):
-        e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e2e_t = []
-    for _ in range(args.steps):
-        flush.fill_(1)
+    def time_e2e(block):
+        for _ in range(warmup):
+            e2e_step(block)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_step()
-        e2e_t.append(time.perf_counter() - t0)
-    t_e2e = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        tt = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_step(block)
+            tt.append(time.perf_counter() - t0)
+        return float(np.mean(tt))
+
+    t_e2e_block = time_e2e(True)
+    t_e2e_scalar = time_e2e(False)
+    t_e2e = torch.tensor([t_e2e_block], dtype=torch.float64, device=dev)
     e2e_value = world * ne / float(t_e2e.item())
     h2d = nodes.nbytes + conn.nbytes
-    d2h = h_indptr.numel() * 8 + h_indices.numel() * 4 + h_values.numel() * 8
+    d2h = h_blkptr.numel() * 8 + h_blkcols.numel() * 4 + h_values.numel() * 8
+    d2h_scalar = h_indptr.numel() * 8 + h_indices.numel() * 4 + h_values.numel() * 8
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     # k_rows (B^T C B products fused with the deterministic row reduction) has the largest share of the step.
@@ -596,21 +577,59 @@ def main():
     peak, peak_src = measured_peaks()
     names = list(pkg.TIMER_NAMES)
     kern_ms = float(ph_mean[names.index("k_rows")])
-    abytes = algorithmic_bytes(w, nnz)
-    achieved = abytes / (kern_ms * 1e-3) / 1e9
     probe = (C.c_double * 2)()
     rc = L.femb200_probe_peaks(ctx_holder.ctx, 5, probe)
-    roofline = {"bound": "hbm", "kernel": "k_rows (B^T C B per scalar CSR row fused with the deterministic segmented reduction)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes": abytes, "kernel_ms": kern_ms,
-                "kernel_share_of_step": kern_ms / dev_ms,
-                "algorithmic_bytes_def": "staged geometry records read + incidence list + element->slot map (pos16) read + CSR values written",
+    p64 = float(probe[0]) if rc == 0 and probe[0] > 0 else 37.2     # TFLOP/s: measured DFMA probe, else 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+    # T_roof = max(F_alg / P64, B_alg / BW) with the DENSE-formulation flops of the reference arithmetic and the
+    # COMPULSORY bytes only (no intermediate of this implementation is counted).
+    shape = w["elemT"]
+    nqp = len(shape.Quadrature()[1])
+    dimC = w["c"].Constitutive().shape[0]
+    dgeo = 3 if w["name"] in ("tetra4", "hexa8", "tetra10", "hexa20") else 2
+    f_elem = dense_flops_per_element(dgeo, nn, w["ndn"], nqp, dimC, w["name"] == "quad4")
+    f_tot = f_elem * ne
+    # dominant kernel (row kernel): it must read the connectivity-sized slot map and the coordinates and write the values
+    kbytes = 4 * nn * ne + 24 * nodes.shape[0] + 8 * nnz
+    k_hbm = kbytes / (kern_ms * 1e-3) / 1e9
+    k_tf = f_tot / (kern_ms * 1e-3) / 1e12
+    t_fp64_ms, t_hbm_ms = f_tot / (p64 * 1e12) * 1e3, kbytes / (peak * 1e9) * 1e3
+    fp64_bound = t_fp64_ms >= t_hbm_ms
+    cbytes = compulsory_bytes(w, nnz, ndof)
+    step_roof_ms = max(f_tot / (p64 * 1e12) * 1e3, cbytes / (peak * 1e9) * 1e3)
+    roofline = {"bound": "fp64" if fp64_bound else "hbm",
+                "kernel": "k_srows_fused (per-element B^T C B per scalar CSR row, geometry recomputed from row-cached coordinates, fused with the "
+                          "deterministic segmented reduction)" if nn <= 4 else "k_noderows (B^T C B per node row fused with the deterministic segmented reduction)",
+                "achieved": k_tf if fp64_bound else k_hbm, "peak": p64 if fp64_bound else peak, "unit": "TFLOP/s" if fp64_bound else "GB/s",
+                "frac": (t_fp64_ms if fp64_bound else t_hbm_ms) / kern_ms, "traffic": None,
+                "peak_source": ("FP64 vector peak measured in this run by femb200_probe_peaks (MEASURED_PEAKS.json holds no FP64 figure)" if fp64_bound else peak_src),
+                "hbm": {"achieved": k_hbm, "peak": peak, "unit": "GB/s", "frac": t_hbm_ms / kern_ms, "peak_source": peak_src,
+                        "algorithmic_bytes": kbytes, "algorithmic_bytes_def": "SURVEY 8(d), compulsory only: int32 connectivity-sized slot map + node coordinates read, CSR values written"},
+                "fp64_dense": {"achieved": k_tf, "peak": p64, "unit": "TFLOP/s", "frac": t_fp64_ms / kern_ms,
+                               "flops_per_element": f_elem, "def": "SURVEY 8(d) F_alg: dense-formulation flops of the reference arithmetic (the kernel exploits B sparsity: fewer are executed)"},
+                "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / dev_ms,
                 "probe_this_run": {"fp64_dfma_tflops": float(probe[0]), "hbm_copy_gbs": float(probe[1])} if rc == 0 else None,
-                "whole_step": {"compulsory_bytes": compulsory_bytes(w, nnz, ndof), "hbm_floor_ms": compulsory_bytes(w, nnz, ndof) / (peak * 1e9) * 1e3,
-                               "frac_of_hbm_roofline": compulsory_bytes(w, nnz, ndof) / (peak * 1e9) * 1e3 / dev_ms}}
+                "whole_step": {"compulsory_bytes": cbytes, "dense_flops": f_tot, "roof_ms": step_roof_ms,
+                               "hbm_floor_ms": cbytes / (peak * 1e9) * 1e3, "fp64_floor_ms": f_tot / (p64 * 1e12) * 1e3,
+                               "frac_of_roofline": step_roof_ms / dev_ms, "frac_of_hbm_roofline": cbytes / (peak * 1e9) * 1e3 / dev_ms}}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_k_rows.json")
     if os.path.exists(traffic_file):
-        roofline["traffic"] = json.load(open(traffic_file)).get(args.config)
+        tf = json.load(open(traffic_file))
+        roofline["traffic"] = tf.get(args.config)
+        roofline["traffic_source"] = tf.get("source")
+
+    # ---- strong-scaling point of the 101 M-element mesh on one GPU (the N > 1 runs report the same mesh over N GPUs) ---------
+    s_line = None
+    if args.config == "tetra4" and not args.size and os.environ.get("FEMB200_BENCH_S", "1") != "0":
+        del flush, h_nodes, h_conn, h_blkptr, h_blkcols, h_values, h_indptr, h_indices, d_nodes, d_conn
+        torch.cuda.empty_cache()
+        try:
+            sres = s_mesh_strong_scaling(pkg, ctx_holder.ctx, desc0, 0, 1, dev)
+            s_line = {"workload": f"Tetra4 BCC N=204: {sres['n_elem']} elements / {sres['n_dofs']} dofs over 1 GPU",
+                      "value": sres["n_elem"] / (sres["ms"] * 1e-3), "unit": "elements/s", "ms_per_step": sres["ms"],
+                      "partition_ms_device_max": sres["partition_ms_device"], "mesh_generation_s_rank0": sres["mesh_generation_s"],
+                      "nnz_total": sres["nnz_rank"], "steps": 3}
+        except Exception as ex:  # reported, not fatal: the headline is config 1
+            s_line = {"error": str(ex)[:300]}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
     cpu = None
@@ -630,9 +649,14 @@ def main():
                 "wall_ms_per_step_host_clock": 1e3 * float(np.mean(wall)),
                 "phases_ms": dict(zip(pkg.TIMER_NAMES, [float(x) for x in ph_mean])),
                 "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": 1e3 * float(t_e2e.item())},
+                        "ms_per_step": 1e3 * float(t_e2e.item()),
+                        "note": "C ABI with pinned host buffers: nodes f64 + int64 connectivity (a Go []int) in; K out as node-block pattern + values "
+                                "(femb200_bsr_copy: blkptr int64, blkcols int32, values f64)",
+                        "scalar_csr_variant": {"value": world * ne / t_e2e_scalar, "ms_per_step": 1e3 * t_e2e_scalar, "d2h_bytes_per_step": d2h_scalar,
+                                               "note": "femb200_csr_copy: indptr int64 + scalar indices int32 + values f64"}},
+                "strong_scaling_S": s_line,
                 "reassemble_cached_pattern": {"value": ne / (re_ms * 1e-3), "unit": "elements/s", "ms_per_step": re_ms,
-                                              "note": "femb200_reassemble: geometry kernel + node-row kernel on the cached symbolic plan (not the headline: "
+                                              "note": "femb200_reassemble: numeric phase only on the cached symbolic plan (not the headline: "
                                                       "the reference rebuilds everything on every call)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "published_go_reference": {"elements_per_s": 39380, "hardware": "AMD Ryzen 5 3400G, README.md:86 (33.0 s for this mesh)"}}

@@ -93,6 +93,7 @@ def lib():
     L.femb200_dist_destroy.argtypes = [vp]
     L.femb200_dist_add_isoparametric.argtypes = [vp, C.POINTER(ElemDesc)]
     L.femb200_dist_last_error.argtypes = [vp, _i32p, _i64p, _i32p]
+    L.femb200_dist_reset.argtypes = [vp]
     L.femb200_dist_assembler.argtypes = [vp]
     L.femb200_dist_assembler.restype = vp
     L.femb200_dist_info.argtypes = [vp, _i64p, C.POINTER(C.c_float)]
@@ -643,6 +644,9 @@ class DistRank:
         k, e, q = C.c_int32(), C.c_int64(), C.c_int32()
         lib().femb200_dist_last_error(self.h, C.byref(k), C.byref(e), C.byref(q))
         return k.value, e.value, q.value
+
+    def reset(self):
+        return lib().femb200_dist_reset(self.h)
 
     def assembler(self):
         return lib().femb200_dist_assembler(self.h)

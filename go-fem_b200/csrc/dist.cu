@@ -356,6 +356,16 @@ int femb200_dist_add_isoparametric(femb200_dist *d, const femb200_elem_desc *des
   return femb200_add_isoparametric(d->ga, desc, d->lconn, 0, 1, d->n_local_elems);
 }
 
+int femb200_dist_reset(femb200_dist *d) {
+  if (!d) return FEMB200_ERR_BAD_ARG;
+  if (d->ga) femb200_assembler_destroy(d->ga);
+  d->ga = nullptr;
+  int rc = femb200_assembler_create(d->ctx, d->lnodes, d->n_local_nodes, d->mdpn, 1, &d->ga);
+  if (rc) return rc;
+  femb200_assembler_set_node_mask_device(d->ga, d->lmask);
+  return femb200_assembler_set_column_map_device(d->ga, d->l2g, d->n_nodes);
+}
+
 femb200_assembler *femb200_dist_assembler(femb200_dist *d) { return d ? d->ga : nullptr; }
 
 int femb200_dist_info(const femb200_dist *d, int64_t out[8], float *partition_ms) {

@@ -206,6 +206,9 @@ void femb200_dist_destroy(femb200_dist *d);
  * lowest failing element of THIS rank in global numbering; the lowest over all ranks is what the reference would report). */
 int femb200_dist_add_isoparametric(femb200_dist *d, const femb200_elem_desc *desc);
 int femb200_dist_last_error(const femb200_dist *d, int32_t *kind, int64_t *elem, int32_t *qp);
+/* Empties the rank's K (a fresh local assembler over the same partition): the next femb200_dist_add_isoparametric starts
+ * from NewGeneralAssembler again instead of accumulating. */
+int femb200_dist_reset(femb200_dist *d);
 femb200_assembler *femb200_dist_assembler(femb200_dist *d);
 /* out = { local nodes, owned nodes, local elements (own + halo), elements of the rank's chunk, halo elements, nnz of the row
  * block, global nodes, global elements }; *partition_ms = device time of the partition (CUDA events). */
