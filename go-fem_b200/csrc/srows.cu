@@ -578,9 +578,12 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
         for (int ii = 0; ii < D; ++ii)
 #pragma unroll
           for (int j = 0; j < D; ++j) {
+            // jac.Mul(dN, X) (:93) exactly as the reference rounds it: node-ascending, multiply and add unfused.  With
+            // coordinates far from the origin (|X| / h ~ 2000 in config 2) the entries of J carry a relative rounding
+            // error of ~|X|/h * eps; only the SAME roundings keep K within 1e-12 of the reference there.
             double sj = 0.0;
 #pragma unroll
-            for (int b = 0; b < NN; ++b) sj = fma(tb.dN[(q * D + ii) * NN + b], X[b][j], sj);
+            for (int b = 0; b < NN; ++b) sj = __dadd_rn(sj, __dmul_rn(tb.dN[(q * D + ii) * NN + b], X[b][j]));
             J[ii][j] = sj;
           }
         const double detJ = inv_lean<D>(J, inv);
