@@ -404,9 +404,19 @@ def run_multi_gpu(args, rank, world, local_rank):
                                 "(indptr int64, global indices int32, values f64) out to pinned host memory; host clock, max over ranks; bytes summed over ranks"},
                 "strong_scaling_S": s_line,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line))
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def _csr_dev(L, h):
@@ -432,6 +442,13 @@ def main():
 
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"   # the version banner goes to stdout; the contract is ONE JSON line
+    # NCCL can still print its version banner from C code at communicator creation: everything this process and its
+    # libraries write to file descriptor 1 goes to stderr, the JSON line alone is written to the real stdout at the end
+    global _REAL_STDOUT
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -667,7 +684,7 @@ def main():
                                                       "the reference rebuilds everything on every call)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "published_go_reference": {"elements_per_s": 39380, "hardware": "AMD Ryzen 5 3400G, README.md:86 (33.0 s for this mesh)"}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
