@@ -42,16 +42,16 @@ __global__ void __launch_bounds__(256) k_peak_dfma(int iters, double *out) {
 }
 
 // ---- the product: one warp = one 32 x 32 block, NQP points, operands staged in shared memory --------------------------
-constexpr int NQP = 27, M = 32, KC = 6, KP = 8;
+constexpr int NQP = 27, NST = 3, M = 32, KC = 6, KP = 8; // NST points staged per warp and cycled (shared-memory budget)
 
 template <bool USE_DMMA>
 __global__ void __launch_bounds__(128) k_btdb(int nblocks_per_warp, const double *__restrict__ gA, const double *__restrict__ gB, double *__restrict__ out) {
   // per warp: A[q][M][KP] (B^T C f, K padded with zeros) and B[q][KP][M]
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *sA = sm + (size_t)warp * (2 * NQP * M * KP);
-  double *sB = sA + NQP * M * KP;
-  for (int i = lane; i < NQP * M * KP; i += 32) { sA[i] = gA[i]; sB[i] = gB[i]; }
+  double *sA = sm + (size_t)warp * (2 * NST * M * KP);
+  double *sB = sA + NST * M * KP;
+  for (int i = lane; i < NST * M * KP; i += 32) { sA[i] = gA[i]; sB[i] = gB[i]; }
   __syncwarp();
   double total = 0.0;
   for (int blk = 0; blk < nblocks_per_warp; ++blk) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128) k_btdb(int nblocks_per_warp, const double
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       const int r = lane >> 2, c = lane & 3;
       for (int q = 0; q < NQP; ++q) {
-        const double *A = sA + q * M * KP, *Bm = sB + q * KP * M;
+        const double *A = sA + (q % NST) * M * KP, *Bm = sB + (q % NST) * KP * M;
 #pragma unroll
         for (int ks = 0; ks < KP / 4; ++ks) {
           double af[4], bf[4];
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) k_btdb(int nblocks_per_warp, const double
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
       const int r0 = 4 * (lane >> 2), c0 = 8 * (lane & 3);
       for (int q = 0; q < NQP; ++q) {
-        const double *A = sA + q * M * KP, *Bm = sB + q * KP * M;
+        const double *A = sA + (q % NST) * M * KP, *Bm = sB + (q % NST) * KP * M;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
           double a[4], b[8];
@@ -144,12 +144,12 @@ int main() {
     printf("peak DFMA        : %.2f TFLOP/s (%.3f ms)\n", fl2 / ms / 1e9, ms);
   }
   {
-    const size_t n = (size_t)NQP * M * KP;
+    const size_t n = (size_t)NST * M * KP;
     double *hA = (double *)malloc(n * 8), *hB = (double *)malloc(n * 8);
     for (size_t i = 0; i < n; ++i) { hA[i] = ((i % KP) < KC) ? 1e-3 * (i % 97) : 0.0; hB[i] = ((i / M) % KP < KC) ? 1e-3 * (i % 89) : 0.0; }
     double *dA, *dB; CK(cudaMalloc(&dA, n * 8)); CK(cudaMalloc(&dB, n * 8));
     CK(cudaMemcpy(dA, hA, n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB, n * 8, cudaMemcpyHostToDevice));
-    const int T = 128, warps = T / 32, per_warp = 200;
+    const int T = 128, warps = T / 32, per_warp = 400;
     const size_t smem = (size_t)warps * 2 * n * 8;
     CK(cudaFuncSetAttribute(k_btdb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_btdb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
