@@ -6,6 +6,19 @@
 
 using namespace femb200;
 
+namespace femb200 {
+__global__ void k_init_call(int64_t *scalars) {
+  if (threadIdx.x < kNumScalars) scalars[threadIdx.x] = threadIdx.x == kScalarErr ? (int64_t)kNoError : 0;
+}
+// zeroes the per-call scalars and arms the error word (one tiny launch instead of a memset per scalar)
+int reset_call_scalars(femb200_ctx *ctx) {
+  k_init_call<<<1, 32, 0, ctx->stream>>>(ctx->d_scalars);
+  ctx->launches++;
+  FEMB_CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+} // namespace femb200
+
 extern "C" {
 
 int femb200_abi_version(void) { return FEMB200_ABI_VERSION; }
@@ -31,10 +44,13 @@ int femb200_ctx_create(int device, femb200_ctx **out) {
   CK(cudaDeviceGetDefaultMemPool(&ctx->pool, device));
   uint64_t thr = UINT64_MAX; // keep freed blocks in the pool: repeated assemblies never hit cudaMalloc
   CK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
-  CK(cudaMalloc((void **)&ctx->d_err, sizeof(unsigned long long)));
-  CK(cudaMalloc((void **)&ctx->d_scalars, 8 * sizeof(int64_t)));
-  CK(cudaMallocHost((void **)&ctx->h_scalars, 8 * sizeof(int64_t)));
-  CK(cudaMallocHost((void **)&ctx->h_err, sizeof(unsigned long long)));
+  // one small device block for every per-call scalar (common.cuh: kScalar*), its pinned mirror, and a pinned staging buffer
+  // for the per-call tables: a call reads all of them back with ONE copy and uploads its tables with ONE copy
+  CK(cudaMalloc((void **)&ctx->d_scalars, kNumScalars * sizeof(int64_t)));
+  CK(cudaMallocHost((void **)&ctx->h_scalars, kNumScalars * sizeof(int64_t)));
+  ctx->d_err = reinterpret_cast<unsigned long long *>(ctx->d_scalars + kScalarErr);
+  ctx->h_err = reinterpret_cast<unsigned long long *>(ctx->h_scalars + kScalarErr);
+  CK(cudaMallocHost((void **)&ctx->h_stage, kStageBytes));
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -51,10 +67,9 @@ void femb200_ctx_destroy(femb200_ctx *ctx) {
   if (ctx->cub_tmp) cudaFreeAsync(ctx->cub_tmp, ctx->stream);
   scratch_release(ctx, true);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->d_err);
   cudaFree(ctx->d_scalars);
   cudaFreeHost(ctx->h_scalars);
-  cudaFreeHost(ctx->h_err);
+  cudaFreeHost(ctx->h_stage);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -235,7 +250,7 @@ static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc
 
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
   *ctx->h_err = kNoError;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+  if ((rc = reset_call_scalars(ctx))) { ga->err_kind = rc; return rc; }
   int32_t *conn32 = nullptr;
   void *staged = nullptr;
   double *d_tab = nullptr;
@@ -259,9 +274,19 @@ static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc
   if (!rc && cudaMemsetAsync(precount, 0, sizeof(int32_t) * 2 * (ga->n_nodes + 1), st) != cudaSuccess) { ctx->last_cuda_error = "cudaMemsetAsync"; rc = FEMB200_ERR_CUDA; }
   if (!rc) rc = stage_conn(ga, conn, conn_is_int64 != 0, conn_on_device != 0, n_elem * sh.nn, sh.nn, &conn32, &staged, precount, sh.nn == 4 && sh.d == 3);
   sym.precount = precount;
-  if (!rc) rc = scratch_alloc(ctx, &d_tab, blob.size());
+  // tables [C | w | N | dN] and the distinct-dof map behind them: ONE upload from the pinned staging buffer
+  const size_t tab_slots = blob.size() + (kMaxNdn * sizeof(int) + sizeof(double) - 1) / sizeof(double);
+  if (!rc) rc = scratch_alloc(ctx, &d_tab, tab_slots);
   if (!rc) {
-    cudaError_t e = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st);
+    cudaError_t e;
+    if (tab_slots * sizeof(double) <= kStageBytes) {
+      std::memcpy(ctx->h_stage, blob.data(), sizeof(double) * blob.size());
+      std::memcpy(ctx->h_stage + sizeof(double) * blob.size(), sh.umap, sizeof(int) * kMaxNdn);
+      e = cudaMemcpyAsync(d_tab, ctx->h_stage, sizeof(double) * tab_slots, cudaMemcpyHostToDevice, st);
+      sym.d_umap = reinterpret_cast<const int *>(d_tab + blob.size());
+    } else {
+      e = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st);
+    }
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
   }
   if (!rc && cudaEventRecord(ctx->ev[1], st) != cudaSuccess) { ctx->last_cuda_error = "cudaEventRecord"; rc = FEMB200_ERR_CUDA; }
@@ -318,8 +343,8 @@ static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc
   if (!rc) {
     cudaError_t e = cudaSuccess;
     if (forked) e = cudaStreamWaitEvent(st, ctx->ev_join, 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) // every scalar of the call (sizes, guard flag, error word) in one copy
+      e = cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, kNumScalars * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st); // blob / caller buffers are released after this point
     if (e != cudaSuccess) { ctx->last_cuda_error = cudaGetErrorString(e); rc = FEMB200_ERR_CUDA; }
@@ -328,7 +353,7 @@ static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc
   if (rc) return fail(rc); // K untouched (:118-120)
   if (sym.speculative) {
     const int64_t real_maxrl = ctx->h_scalars[0], real_nblk = ctx->h_scalars[1];
-    if (ctx->h_scalars[7] != 0 || real_maxrl > sym.max_rowlen || real_nblk > sym.cap_blk || real_maxrl > (int64_t)pos_mask(sh.nn)) {
+    if (ctx->h_scalars[kScalarGuard] != 0 || real_maxrl > sym.max_rowlen || real_nblk > sym.cap_blk || real_maxrl > (int64_t)pos_mask(sh.nn)) {
       ctx->hint.valid = false; // a guard tripped: the mesh is not the one the hint came from
       fail(0);
       return add_isoparametric_impl(ga, desc, conn, conn_is_int64, conn_on_device, n_elem, n_pattern_only, false);
@@ -438,7 +463,7 @@ int femb200_reassemble(femb200_assembler *ga, const femb200_elem_desc *desc, con
   };
   cudaError_t ce;
   *ctx->h_err = kNoError;
-  if ((ce = cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st)) != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
+  if ((rc = reset_call_scalars(ctx))) return fail(rc);
   if ((rc = scratch_alloc(ctx, &d_tab, blob.size()))) return fail(rc);
   if ((ce = cudaMemcpyAsync(d_tab, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(FEMB200_ERR_CUDA, ce);
   if ((rc = dev_alloc(ctx, &newvals, (size_t)ga->K.nnz))) return fail(rc);
@@ -673,7 +698,7 @@ int femb200_isoparametric_strains(femb200_assembler *ga, const femb200_elem_desc
   int rc = prepare(ga, desc, &sh, &blob);
   if (rc) { ga->err_kind = rc; return rc; }
   *ctx->h_err = kNoError;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+  if ((rc = reset_call_scalars(ctx))) { ga->err_kind = rc; return rc; }
   int32_t *conn32 = nullptr, *d_dofmap = nullptr;
   void *staged = nullptr;
   double *d_tab = nullptr, *d_u = nullptr, *d_s = nullptr;

@@ -18,6 +18,9 @@ constexpr int kTabDoubles = 5632; // 44 KB of __constant__ table space (N | dN |
 // Slot map entries pos16[k][b] (row-local block position of node b of the element of incidence k).  For elements with
 // <= 4 nodes the two top bits of entry b = 0 also carry the local index of the row's own node in the element, so the
 // fused scalar-row kernel reads ONE 8-byte word per incident element and never touches the incidence list.
+// Per-call device scalars (ctx->d_scalars, mirrored in pinned ctx->h_scalars and read back with one copy)
+constexpr int kScalarMaxRowlen = 0, kScalarNblk = 1, kScalarGroupNeed = 2 /* ..5 */, kScalarNShort = 6, kScalarGuard = 7, kScalarErr = 8, kNumScalars = 16;
+constexpr size_t kStageBytes = 64 * 1024; // pinned staging buffer of the per-call tables
 constexpr int kPosLaShift = 14;
 constexpr unsigned kPosMask = 0x3fffu;
 __host__ __device__ inline unsigned pos_mask(int nn) { return nn <= 4 ? kPosMask : 0xffffu; }
@@ -86,10 +89,11 @@ struct femb200_ctx {
   std::string last_cuda_error;
   void *cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  unsigned long long *d_err = nullptr;      // device error word
+  unsigned long long *d_err = nullptr;      // device error word (alias of d_scalars + kScalarErr)
   int64_t *d_scalars = nullptr;             // small device scratch (8 x int64)
   int64_t *h_scalars = nullptr;             // pinned host mirror
-  unsigned long long *h_err = nullptr;      // pinned
+  unsigned long long *h_err = nullptr;      // pinned (alias of h_scalars + kScalarErr)
+  char *h_stage = nullptr;                  // pinned staging of the per-call tables
   cudaEvent_t ev[12] = {};
   // second stream: the per-element checks of the fused numeric path run beside the symbolic phase
   cudaStream_t stream2 = nullptr;
@@ -206,6 +210,7 @@ struct SymbolicResult {
   int64_t n_short = 0;        // rows [0, n_short) of `order` have rowlen <= max_rowlen / 2
   int64_t group_need[4] = {0, 0, 0, 0}; // max over aligned groups of 4 / 8 / 16 / 32 consecutive rows of sum(rowlen)
   int32_t *blkcols = nullptr;       // [nblk] column node of every node block
+  const int *d_umap = nullptr;      // distinct-dof map on the device, uploaded with the tables (or NULL: symbolic_phase uploads it)
   int32_t *precount = nullptr;      // [2*(n_nodes+1)] incidence histogram | zeroed fill cursors, taken while narrowing (or NULL)
   bool speculative = false;         // sizes came from ctx->hint: nblk / max_rowlen are capacities until the call's final sync
   int64_t cap_blk = 0;              // capacity (node blocks) of indices / values / blkcols
@@ -220,6 +225,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
 int numeric_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const double *h_tab, int tab_doubles,
                   const int32_t *conn32, int64_t n_elem, SymbolicResult *sym, int64_t n_elem_total);
 bool numeric_supported(const ElemShape &sh);
+int reset_call_scalars(femb200_ctx *ctx);
 int check_phase(femb200_assembler *ga, const ElemShape &sh, const double *d_tab, const int32_t *conn32, int64_t n_elem, cudaStream_t st);
 int csr_merge_into(femb200_assembler *ga, DeviceCsr *add); // K += add (consumes add)
 int csr_accumulate_rows(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, const int64_t *indptr, const int32_t *indices,

@@ -200,7 +200,7 @@ int csr_add_entries(femb200_assembler *ga, int64_t n_rows, const int64_t *rows, 
   if (n_rows == 0) return 0;
   if (ga->K.nnz == 0) return FEMB200_ERR_PATTERN;
   *ctx->h_err = kNoError;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+  if (int rcr = reset_call_scalars(ctx)) return rcr;
   // pass 1 checks that every entry is in the pattern (K untouched on failure), pass 2 adds
   k_add_entries<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(n_rows, rows, indptr, indices, values, ga->K.indptr, ga->K.indices, ga->K.values, ctx->d_err, 1);
   ctx->launches++;

@@ -215,7 +215,7 @@ int femb200_dist_create(femb200_ctx *ctx, int32_t rank, int32_t world, const dou
     femb200_assembler probe; // only n_nodes / ctx are read by the validator
     probe.ctx = ctx; probe.n_nodes = n_nodes;
     *ctx->h_err = kNoError;
-    FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_err, 0xff, sizeof(unsigned long long), st));
+    if (int rcr = reset_call_scalars(ctx)) return rcr;
     if ((rc = narrow_and_validate_conn(&probe, d_in, conn_is_int64 != 0, ninc, nn, conn32))) return rc;
     FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     FEMB_CUDA_OK(ctx, cudaStreamSynchronize(st));

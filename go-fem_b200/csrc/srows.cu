@@ -727,11 +727,11 @@ int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const d
   FusedIn fi;
   fi.nodes4 = nodes4; fi.blkcols = blkcols; fi.rl_cap = 0;
   fi.cap_blk = cap_blk; fi.guard = (unsigned long long *)(ctx->d_scalars + 7);
-  const int tpb = getenv("FEMB200_SROW_TPB") ? atoi(getenv("FEMB200_SROW_TPB")) : 64; // 64-thread blocks: finer shared-memory granularity than 128
+  const int tpb = getenv("FEMB200_SROW_TPB") ? atoi(getenv("FEMB200_SROW_TPB")) : 32; // one warp per block: finest shared-memory granularity (measured 2-3 % over 64)
 #define FEMB_F(Dv, NNv, BK)                                                                                          \
-  return tpb == 32    ? launch_fused_T<Dv, NNv, BK, 32>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap)            \
+  return tpb == 64    ? launch_fused_T<Dv, NNv, BK, 64>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap)            \
          : tpb == 128 ? launch_fused_T<Dv, NNv, BK, 128>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap)           \
-                      : launch_fused_T<Dv, NNv, BK, 64>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap)
+                      : launch_fused_T<Dv, NNv, BK, 32>(ctx, sh, a, fi, h_tab, order, v0, v1, rowlen_cap)
   switch (sh.bkind) {
   case FEMB200_B_XYZ: if (sh.nn == 4) FEMB_F(3, 4, FEMB200_B_XYZ); break;
   case FEMB200_B_PLANE: if (sh.nn == 4) FEMB_F(2, 4, FEMB200_B_PLANE); if (sh.nn == 3) FEMB_F(2, 3, FEMB200_B_PLANE); break;

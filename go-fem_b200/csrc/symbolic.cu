@@ -115,6 +115,7 @@ k_row_pattern(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32_t *__
   const int T = blockDim.x, tid = threadIdx.x;
   int64_t I = (int64_t)blockIdx.x * T + tid;
   if (I >= n_nodes) return;
+  if (I == 0) rowlen[n_nodes] = 0;                           // tail entry of the scan input
   if (node_mask && !node_mask[I]) { rowlen[I] = 0; return; } // row not assembled on this rank
   if (only_flagged && rowlen[I] >= 0) return; // already done by k_row_pattern_group
   const int beg = n2e_ptr[I], end = n2e_ptr[I + 1];
@@ -199,6 +200,7 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   int32_t *ul = reinterpret_cast<int32_t *>(lst + MAXINC);
   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + tid) / G;
   if (I >= n_nodes) return;
+  if (I == 0 && l == 0) rowlen[n_nodes] = 0;                              // tail entry of the scan input
   if (only_flagged && rowlen[I] >= 0) return;                             // done by the previous (cheaper) pass
   if (node_mask && !node_mask[I]) { if (l == 0) rowlen[I] = 0; return; } // row not assembled on this rank
   const int gshift = (tid & 31) & ~(G - 1);
@@ -449,7 +451,8 @@ template <int NU>
 __global__ void __launch_bounds__(256)
 k_expand8(int64_t n_nodes, int nn, const int32_t *__restrict__ n2e_ptr, const int64_t *__restrict__ blkptr,
           const int32_t *__restrict__ tmpcols, int32_t *__restrict__ indices, int64_t *__restrict__ indptr,
-          const int32_t *__restrict__ col_map, int32_t *__restrict__ blkcols, int64_t cap_blk, unsigned long long *__restrict__ guard) {
+          const int32_t *__restrict__ col_map, int32_t *__restrict__ blkcols, int64_t cap_blk, unsigned long long *__restrict__ guard,
+          int64_t *__restrict__ scalars) {
   constexpr int R = 8;
   const int lane = threadIdx.x & 31;
   const int64_t I0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R;
@@ -466,7 +469,16 @@ k_expand8(int64_t n_nodes, int nn, const int32_t *__restrict__ n2e_ptr, const in
 #pragma unroll
     for (int i = 0; i < NU; ++i) indptr[(I0 + lane) * NU + i] = (int64_t)NU * NU * bp + (int64_t)i * rl_mine * NU;
   }
-  if (I0 + nrow == n_nodes && lane == nrow) indptr[n_nodes * NU] = (int64_t)NU * NU * bp;
+  if (I0 + nrow == n_nodes && lane == nrow) {
+    indptr[n_nodes * NU] = (int64_t)NU * NU * bp;
+    scalars[kScalarNblk] = bp;                                   // node blocks of the call
+  }
+  {                                                              // max row length of the call: warp max, one atomic per warp
+    int mx = rl_mine;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx > 0) atomicMax(reinterpret_cast<unsigned long long *>(scalars + kScalarMaxRowlen), (unsigned long long)mx);
+  }
   const bool over = lane < nrow && bp + rl_mine > cap_blk;
   if (__any_sync(0xffffffffu, over)) { if (lane == 0) atomicOr(guard, 1ull); return; } // hinted capacity exceeded: the call is repeated
   int32_t colreg[R];
@@ -595,7 +607,6 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   int32_t *tmpcols = nullptr;
   if ((rc = scratch_alloc(ctx, &tmpcols, ninc * nn))) return rc;
   if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn))) return rc;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(rowlen + n_nodes, 0, sizeof(int64_t), st));
   switch (nn) {
   case 3: rc = launch_row_pattern<3>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
   case 4: rc = launch_row_pattern<4>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
@@ -607,16 +618,21 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   if (rc) return rc;
   // per-group shared-memory need of the numeric phase (rows are visited in node order: a visiting order by first
   // incident element was measured and rejected -- it mixes rows with 5 and with 24 incident elements in one warp)
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scalars + 2, 0, 4 * sizeof(int64_t), st));
   if (n_nodes && (nn == 8 || nn == 20)) { // the element sizes whose numeric kernel uses packed accumulators
     k_group_need<<<grid_for(n_nodes, 256), 256, 0, st>>>(n_nodes, rowlen, (unsigned long long *)(ctx->d_scalars + 2));
     ctx->launches++;
   }
   tb = ctx->cub_tmp_bytes;
   FEMB_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, rowlen, out->blkptr, (int)(n_nodes + 1), st));
-  tb = ctx->cub_tmp_bytes;
-  FEMB_CUDA_OK(ctx, cub::DeviceReduce::Max(ctx->cub_tmp, tb, rowlen, ctx->d_scalars, (int)(n_nodes + 1), st));
-  ctx->launches += 4;
+  ctx->launches += 2;
+  // a call sized from a hint needs no scalar before its end: k_expand8 leaves max(rowlen) and the block count in the
+  // per-call scalars, which the caller reads back once; otherwise: CUB max + the small copies the host waits for
+  const bool scalars_from_expand = use_hint && sh.identity && sh.nu <= 3 && ctx->hint.max_rowlen <= 32 && nn != 10 && !getenv("FEMB200_NO_EXPAND8");
+  if (!scalars_from_expand) {
+    tb = ctx->cub_tmp_bytes;
+    FEMB_CUDA_OK(ctx, cub::DeviceReduce::Max(ctx->cub_tmp, tb, rowlen, ctx->d_scalars, (int)(n_nodes + 1), st));
+    ctx->launches += 2;
+  }
   if (nn == 10 && n_nodes && !getenv("FEMB200_ONE_CLASS")) { // two-class visiting order (see k_class_flags)
     uint8_t *flag = nullptr;
     if ((rc = scratch_alloc(ctx, &flag, n_nodes))) return rc;
@@ -630,14 +646,17 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
     FEMB_CUDA_OK(ctx, cub::DevicePartition::Flagged(ctx->cub_tmp, tb, ids, flag, out->order, ctx->d_scalars + 6, (int)n_nodes, st));
     ctx->launches += 3;
   }
-  // host needs nblk (allocation sizes), max row length (numeric launch shape) and the error word
-  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 1, out->blkptr + n_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (!use_hint) {
+    // host needs nblk (allocation sizes), max row length (numeric launch shape) and the error word
+    FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 1, out->blkptr + n_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  } else if (!scalars_from_expand) {
+    FEMB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scalars + kScalarNblk, out->blkptr + n_nodes, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  }
   FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], st));
   if (fork_at == 3 && fork_fn && (rc = (*fork_fn)())) return rc;
-  FEMB_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(int64_t), st)); // capacity-guard flag
   if (use_hint) {
     // sizes from the previous call with this mesh signature; verified by the caller after the call's only synchronisation
     out->speculative = true;
@@ -667,17 +686,21 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   if ((rc = dev_alloc(ctx, &out->blkcols, (size_t)out->nblk))) return rc;
   unsigned umask = 0;
   for (int i = 0; i < nu; ++i) umask |= 1u << sh.umap[i];
-  int *d_umap = nullptr;
-  if ((rc = scratch_alloc(ctx, &d_umap, kMaxNdn))) return rc;
-  FEMB_CUDA_OK(ctx, cudaMemcpyAsync(d_umap, sh.umap, sizeof(int) * kMaxNdn, cudaMemcpyHostToDevice, st));
+  const int *d_umap = out->d_umap;                              // normally uploaded with the tables (api.cu)
+  if (!d_umap) {
+    int *um = nullptr;
+    if ((rc = scratch_alloc(ctx, &um, kMaxNdn))) return rc;
+    FEMB_CUDA_OK(ctx, cudaMemcpyAsync(um, sh.umap, sizeof(int) * kMaxNdn, cudaMemcpyHostToDevice, st));
+    d_umap = um;
+  }
   const bool expand8 = sh.identity && nu <= 3 && out->max_rowlen <= 32 && out->nblk > 0 && !getenv("FEMB200_NO_EXPAND8");
   if (expand8) {
     const unsigned eg = grid_for(((n_nodes + 7) / 8) * 32, 256);
     unsigned long long *guard = (unsigned long long *)(ctx->d_scalars + 7);
     switch (nu) {
-    case 1: k_expand8<1><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard); break;
-    case 2: k_expand8<2><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard); break;
-    default: k_expand8<3><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard); break;
+    case 1: k_expand8<1><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
+    case 2: k_expand8<2><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
+    default: k_expand8<3><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
     }
     ctx->launches++;
   } else {
