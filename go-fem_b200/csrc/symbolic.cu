@@ -218,6 +218,8 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
     lst[idx] = tv[s];                                            // MAXINC entries: the tail is padding that ranks above everything
   }
   __syncwarp(gmask);
+  // (A look-before-sorting test -- is the list already ascending? -- was measured: the atomic fill leaves almost no list in
+  // order, not even the warp-aggregated one, so the look is pure overhead.)
   {
     int rr[IPL];
 #pragma unroll
@@ -234,11 +236,11 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
         rk[rr[s]] = (int32_t)tv[s];
         n2e_t[beg + rr[s]] = tv[s];
       }
-  }
-  __syncwarp(gmask);
+    __syncwarp(gmask);
 #pragma unroll
-  for (int s = 0; s < IPL; ++s) tv[s] = (l + G * s < m) ? (uint32_t)rk[l + G * s] : 0xffffffffu;
-  __syncwarp(gmask);
+    for (int s = 0; s < IPL; ++s) tv[s] = (l + G * s < m) ? (uint32_t)rk[l + G * s] : 0xffffffffu;
+    __syncwarp(gmask);
+  }
 
   // 2. connectivity of my incidences
   int32_t cj[IPL][NN];
@@ -477,7 +479,10 @@ k_expand8(int64_t n_nodes, int nn, const int32_t *__restrict__ n2e_ptr, const in
     int mx = rl_mine;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0 && mx > 0) atomicMax(reinterpret_cast<unsigned long long *>(scalars + kScalarMaxRowlen), (unsigned long long)mx);
+    // look before the atomic: after the first few warps the maximum is already there (one same-address atomic per warp cost
+    // Quad4 0.13 ms)
+    if (lane == 0 && mx > 0 && (int64_t)mx > *reinterpret_cast<volatile int64_t *>(scalars + kScalarMaxRowlen))
+      atomicMax(reinterpret_cast<unsigned long long *>(scalars + kScalarMaxRowlen), (unsigned long long)mx);
   }
   const bool over = lane < nrow && bp + rl_mine > cap_blk;
   if (__any_sync(0xffffffffu, over)) { if (lane == 0) atomicOr(guard, 1ull); return; } // hinted capacity exceeded: the call is repeated
