@@ -160,6 +160,30 @@ __device__ __forceinline__ void srow_copy_out_chunked(const double *acc_w, doubl
   }
 }
 
+// ---- bulk asynchronous copies (TMA) + mbarrier, used to stage the slot-map words of the next eight incident elements -----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar)) : "memory");
+}
+
 struct SRowExtra {
   int cap_m;        // accumulator entries per thread (rl_cap * NDN)
   int stage_cap;    // doubles of copy-out staging per warp
@@ -399,7 +423,7 @@ template <> __device__ __forceinline__ double inv_lean<3>(const double (&J)[3][3
 // node), which makes the diagonal block a compile-time target: it stays in registers for the whole row and only NN-1
 // blocks per element go through shared memory.  (A cyclic shift of 4 vertices is an odd permutation: the determinant
 // changes sign with the parity of the shift, the gradients do not.)
-template <int D, int NN, int BKIND, int NQP, bool SIMPLEX, int TPB>
+template <int D, int NN, int BKIND, int NQP, bool SIMPLEX, int TPB, bool STAGE_POS>
 __global__ void __launch_bounds__(TPB)
 k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedTab tb) {
   using B = BT<BKIND, D>;
@@ -410,7 +434,7 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
   extern __shared__ double s_mem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // per warp: accumulators acc_w[m * 32 + lane] (bank = lane: conflict free whatever the slot), then the coordinate cache
-  double *const acc_w = s_mem + (size_t)warp * ((size_t)x.cap_m * 32 + x.stage_cap);
+  double *const acc_w = s_mem + (size_t)warp * ((size_t)x.cap_m * 32 + x.stage_cap + (STAGE_POS ? 2 * NPW * 8 + 2 : 0));
   double *const s_stage = acc_w + (size_t)x.cap_m * 32;
   const bool act = lane < NSR;
   const int r = lane / NDN, i = lane - r * NDN;
@@ -472,12 +496,9 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
   if (a.has_halo) {
     while (end > beg && (int64_t)(__ldg(a.n2e_t + end - 1) / NN) >= a.n_numeric) --end;
   }
-  unsigned long long wn = 0ull;
-  if (beg < end) load_pos(beg, wn);
-  for (int k = beg; k < end; ++k) {
-    const unsigned long long w64 = wn;
+  // one incident element of my row, given its slot-map word
+  auto element = [&](const unsigned long long w64) {
     const int la = (int)((w64 >> kPosLaShift) & 3u);
-    if (k + 1 < end) load_pos(k + 1, wn);
     if constexpr (SIMPLEX) {
       // rotated order: node b' of this visit = element node (la + b') mod NN; b' = 0 is node I itself
       int pr[NN];
@@ -646,6 +667,52 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
         for (int j = 0; j < NDN; ++j) sp[j * AS] += blk[b][j];
       }
     }
+  };
+  if constexpr (STAGE_POS) {
+    // Slot-map words through shared memory: the words of a row are contiguous (8 bytes per incident element), so the next
+    // EIGHT steps of every row of the warp arrive as one 64-byte bulk asynchronous copy per row (cp.async.bulk, completion
+    // on an mbarrier), double buffered.  The step loop is warp-uniform; a row whose list starts at an odd incidence begins
+    // one slot into its first (16-byte aligned) chunk.
+    static_assert(!STAGE_POS || NN == 4, "staged slot words: 8 bytes per incidence");
+    uint64_t *const posbuf = reinterpret_cast<uint64_t *>(s_stage + x.stage_cap);      // [2][NPW][8]
+    uint64_t *const bars = posbuf + 2 * NPW * 8;                                        // [2]
+    const int off = beg & 1;
+    const int nsteps = (end > beg) ? (end - beg) + off : 0;
+    int maxs = nsteps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxs = max(maxs, __shfl_xor_sync(0xffffffffu, maxs, o));
+    const int nchunks = (maxs + 7) >> 3;
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const uint16_t *const src0 = a.pos16 + (int64_t)(beg - off) * NN;
+    auto issue = [&](int c) {
+      const bool prod = act && i == 0 && 8 * c < nsteps;
+      const unsigned np = __popc(__ballot_sync(0xffffffffu, prod));
+      if (lane == 0) mbar_expect_tx(&bars[c & 1], np * 64u);
+      __syncwarp();
+      if (prod) bulk_g2s(posbuf + ((c & 1) * NPW + r) * 8, src0 + (int64_t)c * 8 * NN, 64u, &bars[c & 1]);
+    };
+    if (nchunks > 0) issue(0);
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&bars[c & 1], (uint32_t)((c >> 1) & 1));
+      __syncwarp();                                               // every lane is done with chunk c-1: its buffer can be refilled
+      if (c + 1 < nchunks) issue(c + 1);
+      const uint64_t *const mine = posbuf + ((c & 1) * NPW + (act ? r : 0)) * 8;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        const int sp = 8 * c + j;
+        if (sp >= off && sp < nsteps) element(mine[j]);
+      }
+    }
+  } else {
+    unsigned long long wn = 0ull;
+    if (beg < end) load_pos(beg, wn);
+    for (int k = beg; k < end; ++k) {
+      const unsigned long long w64 = wn;
+      if (k + 1 < end) load_pos(k + 1, wn);
+      element(w64);
+    }
   }
   if constexpr (SIMPLEX) {
     if (rowsz) {
@@ -679,7 +746,11 @@ static int launch_fused_T(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &
   if (cache < 32) cache = 32;                                    // the in-place copy-out pads every scalar row to an odd length
   if (x.cap_m > 48 && cache < 32 * 17) cache = 32 * 17;          // long rows: chunked copy-out staging
   x.stage_cap = (cache + 1) & ~1;
-  const size_t smem = (size_t)NWARP * ((size_t)x.cap_m * 32 + x.stage_cap) * sizeof(double);
+  // measured (config 1 / config 2): 0.263 vs 0.230 ms and 1.477 vs 1.400 ms WITH the staging -- the warp-uniform chunk loop and
+  // the mbarrier waits cost more than the 8 wavefronts per step the bulk copies save; opt-in for experiments only
+  const bool stage_pos = NN == 4 && getenv("FEMB200_STAGE_POS") != nullptr;
+  const size_t pos_doubles = stage_pos ? (2 * NPW * 8 + 2) : 0;   // staged slot words + two mbarriers per warp
+  const size_t smem = (size_t)NWARP * ((size_t)x.cap_m * 32 + x.stage_cap + pos_doubles) * sizeof(double);
   if (smem > ctx->smem_optin) return -2;
   FusedTab tb;
   TabLayout tl = tab_layout(sh.d, sh.nn, sh.nqp, sh.dimC);
@@ -710,12 +781,22 @@ static int launch_fused_T(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &
     FEMB_CUDA_OK(ctx, cudaGetLastError());
     return 0;
   };
-  if constexpr (NN == D + 1 && !B::RADIAL && B::NV == D) {
-    if (simplex) return go(k_srows_fused<D, NN, BKIND, 1, true, TPB>);
+  if constexpr (NN == 4) {
+    if (stage_pos) {
+      if constexpr (NN == D + 1 && !B::RADIAL && B::NV == D) {
+        if (simplex) return go(k_srows_fused<D, NN, BKIND, 1, true, TPB, true>);
+      }
+      if (sh.nqp == 1) return go(k_srows_fused<D, NN, BKIND, 1, false, TPB, true>);
+      if (sh.nqp == 4) return go(k_srows_fused<D, NN, BKIND, 4, false, TPB, true>);
+      return go(k_srows_fused<D, NN, BKIND, 0, false, TPB, true>);
+    }
   }
-  if (sh.nqp == 1) return go(k_srows_fused<D, NN, BKIND, 1, false, TPB>);
-  if (sh.nqp == 4) return go(k_srows_fused<D, NN, BKIND, 4, false, TPB>);
-  return go(k_srows_fused<D, NN, BKIND, 0, false, TPB>);
+  if constexpr (NN == D + 1 && !B::RADIAL && B::NV == D) {
+    if (simplex) return go(k_srows_fused<D, NN, BKIND, 1, true, TPB, false>);
+  }
+  if (sh.nqp == 1) return go(k_srows_fused<D, NN, BKIND, 1, false, TPB, false>);
+  if (sh.nqp == 4) return go(k_srows_fused<D, NN, BKIND, 4, false, TPB, false>);
+  return go(k_srows_fused<D, NN, BKIND, 0, false, TPB, false>);
 }
 
 // fused front end for elements with <= 4 nodes; returns -2 when it does not apply

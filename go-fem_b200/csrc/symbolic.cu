@@ -611,7 +611,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   // ---- node-block row pattern ----------------------------------------------------------------
   int32_t *tmpcols = nullptr;
   if ((rc = scratch_alloc(ctx, &tmpcols, ninc * nn))) return rc;
-  if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn))) return rc;
+  if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn + 64))) return rc; // + 64: the numeric kernel stages whole 64-byte chunks of slot words
   switch (nn) {
   case 3: rc = launch_row_pattern<3>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
   case 4: rc = launch_row_pattern<4>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
