@@ -730,3 +730,103 @@ def test_keep_rows_then_reassemble_is_refused(pkg, meshes):
     with pytest.raises(RuntimeError):
         ra.bsr()
     ra.close()
+
+
+# ---- paths the structured meshes never reach: long rows, many incidences per node, hint retry -------------------------
+def _fan_triangles(nfan, r0=50.0):
+    """A fan of `nfan` triangles around one centre node plus a second ring: the centre row has nfan + 1 node blocks and
+    nfan incident elements (long-row copy-out of the fused kernel, > 32 incidences: sorted-insert pattern fallback)."""
+    ang = 2 * np.pi * np.arange(nfan) / nfan
+    ring1 = np.stack([r0 + 1.0 * np.cos(ang), 30 + 1.0 * np.sin(ang), np.zeros(nfan)], axis=1)
+    ring2 = np.stack([r0 + 2.0 * np.cos(ang + 0.1), 30 + 2.0 * np.sin(ang + 0.1), np.zeros(nfan)], axis=1)
+    nodes = np.concatenate([[[r0, 30.0, 0.0]], ring1, ring2], axis=0)
+    tris = []
+    for k in range(nfan):
+        a, b = 1 + k, 1 + (k + 1) % nfan
+        tris.append([0, a, b])                                     # inner fan (counter-clockwise)
+        c, d = 1 + nfan + k, 1 + nfan + (k + 1) % nfan
+        tris.append([a, c, b])
+        tris.append([b, c, d])
+    return nodes, np.array(tris, dtype=np.int64)
+
+
+def _cone_tets(nfan):
+    """`nfan` tetrahedra around a vertical axis (two apex nodes shared by all of them): the apex rows have nfan + 2 blocks."""
+    ang = 2 * np.pi * np.arange(nfan) / nfan
+    ring = np.stack([np.cos(ang), np.sin(ang), 0.1 * np.cos(3 * ang)], axis=1)
+    nodes = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], ring], axis=0)
+    tets = [[0, 1, 2 + k, 2 + (k + 1) % nfan] for k in range(nfan)]
+    nodes, tets = np.asarray(nodes, dtype=np.float64), np.array(tets, dtype=np.int64)
+    p = nodes[tets]
+    neg = np.linalg.det(p[:, 1:4, :] - p[:, 0:1, :]) < 0
+    tets[neg, 2], tets[neg, 3] = tets[neg, 3].copy(), tets[neg, 2].copy()
+    return nodes, tets
+
+
+@pytest.mark.parametrize("case", ["tri_fan_20_plane", "tri_fan_40_axisym", "tri_fan_70_plane", "tet_cone_12", "tet_cone_30", "tet_cone_45"])
+def test_long_rows_and_high_valence(pkg, O, case):
+    kind, n = case.split("_")[0], int(case.split("_")[2])
+    if kind == "tri":
+        nodes, conn = _fan_triangles(n)
+        axis = case.endswith("axisym")
+        elemT, okind = pkg.elements.Triangle3(), O.TRIANGLE3
+        c = pkg.solids.Isotropic(210e3, 0.3).Axisymmetric() if axis else pkg.solids.Isotropic(210e3, 0.3).PlaneStrain()
+        flags, mode = 3, (1 if axis else 3)
+        Cm, bk = O.constitutive(mode, 210e3, 0.3)
+    else:
+        nodes, conn = _cone_tets(n)
+        elemT, okind, c, flags = pkg.elements.Tetra4(), O.TETRA4, pkg.solids.Isotropic(200e9, 0.3).Solid3D(), 7
+        Cm, bk = O.constitutive(0, 200e9, 0.3)
+    ga = pkg.fem.NewGeneralAssembler(nodes, flags)
+    err = ga.AddIsoparametric(elemT, c, len(conn), conn)
+    assert err is None, err.msg
+    got = ga.Ksolid().csr()
+    og = O.GeneralAssembler(nodes, flags)
+    og.add_isoparametric(okind, Cm, bk, conn)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    compare_csr(got, (rp, ri, rv), ab, TOL)
+    mdpn = bin(flags).count("1")
+    longest = int(np.diff(rp).max()) // mdpn
+    assert longest >= (n + 1 if kind == "tri" else n + 2)
+
+
+def test_size_hint_of_another_mesh_is_caught_and_the_call_repeated(pkg, O):
+    """The context sizes a call from its previous call with the same (nodes, elements, nn) signature.  Two different meshes
+    with that signature but different row lengths / block counts must both come out right: every kernel guards its writes
+    against the hinted capacities and a tripped guard repeats the call without the hint."""
+    # mesh A: 40 triangles in two separate fans of 20; mesh B: one fan of 40 -- same node and element counts
+    def two_fans():
+        na, ca = _fan_triangles(20)
+        keep = ca[::3]                                             # inner fans only
+        nb = na.copy(); nb[:, 0] += 10.0
+        nodes = np.concatenate([na, nb], axis=0)
+        return nodes, np.concatenate([keep, keep + na.shape[0]], axis=0)
+
+    def one_fan():
+        n1, c1 = _fan_triangles(40)
+        nodes = np.concatenate([n1, n1[:1] + 5.0], axis=0)         # pad to the same node count with an unreferenced node
+        return nodes, c1[::3]
+
+    (nA, cA), (nB, cB) = two_fans(), one_fan()
+    assert nA.shape == nB.shape and cA.shape == cB.shape
+    c = pkg.solids.Isotropic(210e3, 0.3).PlaneStrain()
+    Cm, bk = O.constitutive(3, 210e3, 0.3)
+    ra = pkg.RawAssembler(nA, 2)                                   # ONE context for all calls: the hint persists
+    desc = ra.make_desc(pkg.elements.Triangle3(), c)
+    L = pkg.lib()
+    import ctypes as C
+    for nodes, conn in ((nA, cA), (nA, cA), (nB, cB), (nB, cB), (nA, cA)):
+        h = C.c_void_p()
+        nodes = np.ascontiguousarray(nodes)
+        assert L.femb200_assembler_create(ra.ctx, nodes.ctypes.data, nodes.shape[0], 2, 0, C.byref(h)) == 0
+        c32 = np.ascontiguousarray(conn, dtype=np.int32)
+        assert L.femb200_add_isoparametric(h, C.byref(desc), c32.ctypes.data, 0, 0, conn.shape[0]) == 0
+        n, nnz = L.femb200_total_dofs(h), L.femb200_nnz(h)
+        ip, ix, v = np.zeros(n + 1, dtype=np.int64), np.zeros(nnz, dtype=np.int32), np.zeros(nnz)
+        assert L.femb200_csr_copy(h, ip.ctypes.data, ix.ctypes.data, v.ctypes.data) == 0
+        L.femb200_assembler_destroy(h)
+        og = O.GeneralAssembler(nodes, 3)
+        og.add_isoparametric(O.TRIANGLE3, Cm, bk, conn)
+        rp, ri, rv, ab = og.csr(with_absum=True)
+        compare_csr((ip, ix, v), (rp, ri, rv), ab, TOL)
+    ra.close()
