@@ -390,9 +390,14 @@ struct FusedIn {
   unsigned long long *guard;            // set when a row does not fit the hinted sizes (the call is then repeated)
 };
 
+// a*b - c*d with both products rounded BEFORE the subtraction (never contracted into an FMA): when the two products are
+// equal -- the symmetric cancellations behind the structural zeros of K on axis-aligned or axisymmetric meshes -- the
+// result is exactly 0, as in the reference's unfused arithmetic; fma(a, b, -(c*d)) would leave the rounding residual of c*d.
+__device__ __forceinline__ double diff_of_products(double a, double b, double c, double d) { return __dsub_rn(__dmul_rn(a, b), __dmul_rn(c, d)); }
+
 template <int D> __device__ __forceinline__ double inv_lean(const double (&J)[D][D], double (&inv)[D][D]);
 template <> __device__ __forceinline__ double inv_lean<2>(const double (&J)[2][2], double (&inv)[2][2]) {
-  const double det = fma(J[0][0], J[1][1], -(J[0][1] * J[1][0]));
+  const double det = diff_of_products(J[0][0], J[1][1], J[0][1], J[1][0]);
   const double r = 1.0 / det;
   inv[0][0] = J[1][1] * r; inv[0][1] = -J[0][1] * r;
   inv[1][0] = -J[1][0] * r; inv[1][1] = J[0][0] * r;
@@ -404,9 +409,9 @@ template <> __device__ __forceinline__ double inv_lean<3>(const double (&J)[3][3
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-    c[k][0] = fma(J[k1][1], J[k2][2], -(J[k1][2] * J[k2][1]));
-    c[k][1] = fma(J[k1][2], J[k2][0], -(J[k1][0] * J[k2][2]));
-    c[k][2] = fma(J[k1][0], J[k2][1], -(J[k1][1] * J[k2][0]));
+    c[k][0] = diff_of_products(J[k1][1], J[k2][2], J[k1][2], J[k2][1]);
+    c[k][1] = diff_of_products(J[k1][2], J[k2][0], J[k1][0], J[k2][2]);
+    c[k][2] = diff_of_products(J[k1][0], J[k2][1], J[k1][1], J[k2][0]);
   }
   const double det = fma(J[0][0], c[0][0], fma(J[0][1], c[0][1], J[0][2] * c[0][2]));
   const double r = 1.0 / det;
@@ -521,13 +526,13 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
 #pragma unroll
         for (int kk = 0; kk < 3; ++kk) {
           const int k1 = (kk + 1) % 3, k2 = (kk + 2) % 3;
-          c[kk + 1][0] = fma(ed[k1][1], ed[k2][2], -(ed[k1][2] * ed[k2][1]));
-          c[kk + 1][1] = fma(ed[k1][2], ed[k2][0], -(ed[k1][0] * ed[k2][2]));
-          c[kk + 1][2] = fma(ed[k1][0], ed[k2][1], -(ed[k1][1] * ed[k2][0]));
+          c[kk + 1][0] = diff_of_products(ed[k1][1], ed[k2][2], ed[k1][2], ed[k2][1]);
+          c[kk + 1][1] = diff_of_products(ed[k1][2], ed[k2][0], ed[k1][0], ed[k2][2]);
+          c[kk + 1][2] = diff_of_products(ed[k1][0], ed[k2][1], ed[k1][1], ed[k2][0]);
         }
         det = fma(ed[0][0], c[1][0], fma(ed[0][1], c[1][1], ed[0][2] * c[1][2]));
       } else {
-        det = fma(ed[0][0], ed[1][1], -(ed[0][1] * ed[1][0]));
+        det = diff_of_products(ed[0][0], ed[1][1], ed[0][1], ed[1][0]);
         c[1][0] = ed[1][1]; c[1][1] = -ed[1][0];
         c[2][0] = -ed[0][1]; c[2][1] = ed[0][0];
       }
