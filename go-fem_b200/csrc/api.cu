@@ -55,6 +55,8 @@ int femb200_ctx_create(int device, femb200_ctx **out) {
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
 #undef CK
   *out = ctx;
   return 0;
@@ -74,6 +76,8 @@ void femb200_ctx_destroy(femb200_ctx *ctx) {
   if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+  if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -343,6 +347,7 @@ static int add_isoparametric_impl(femb200_assembler *ga, const femb200_elem_desc
   if (!rc) {
     cudaError_t e = cudaSuccess;
     if (forked) e = cudaStreamWaitEvent(st, ctx->ev_join, 0);
+    if (e == cudaSuccess && sym.expand_forked) e = cudaStreamWaitEvent(st, ctx->ev_join2, 0);
     if (e == cudaSuccess) // every scalar of the call (sizes, guard flag, error word) in one copy
       e = cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, kNumScalars * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], st);

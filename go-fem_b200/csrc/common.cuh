@@ -97,7 +97,8 @@ struct femb200_ctx {
   cudaEvent_t ev[12] = {};
   // second stream: the per-element checks of the fused numeric path run beside the symbolic phase
   cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;       // per-element checks beside the row-pattern kernel
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;     // CSR expansion beside the numeric kernel
   // Sizes of the previous successful call with the same mesh signature.  A call that finds a matching hint sizes its CSR
   // arrays and launch shapes from it and does NOT wait for the device between the symbolic and the numeric phase; the
   // kernels guard every write against the hinted capacities and the call is repeated the slow way if a guard tripped.
@@ -212,6 +213,9 @@ struct SymbolicResult {
   int32_t *blkcols = nullptr;       // [nblk] column node of every node block
   const int *d_umap = nullptr;      // distinct-dof map on the device, uploaded with the tables (or NULL: symbolic_phase uploads it)
   int32_t *precount = nullptr;      // [2*(n_nodes+1)] incidence histogram | zeroed fill cursors, taken while narrowing (or NULL)
+  bool expand_forked = false;       // k_expand8 was queued on the second stream: the caller joins ev_join2 before it reads K
+  const int32_t *rowcols = nullptr; // ascending column nodes of row I at rowcols[cols_stride * n2e_ptr[I] ...] (call scratch)
+  int cols_stride = 0;
   bool speculative = false;         // sizes came from ctx->hint: nblk / max_rowlen are capacities until the call's final sync
   int64_t cap_blk = 0;              // capacity (node blocks) of indices / values / blkcols
   DeviceCsr csr; // indptr + indices filled, values allocated (uninitialised)

@@ -576,7 +576,8 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
       a.stag = nullptr; a.degen = nullptr; a.order = nullptr; a.v0 = 0; a.v1 = ga->n_nodes; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
       a.has_halo = n_elem < n_elem_total ? 1 : 0;
       for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = i < sh.dimC * sh.dimC ? h_tab[i] : 0.0;
-      rc = srows_fused(ctx, sh, a, ga->d_nodes, sym->blkcols, h_tab, nullptr, 0, ga->n_nodes, sym->max_rowlen, nodes4, sym->cap_blk);
+      rc = srows_fused(ctx, sh, a, ga->d_nodes, sym->blkcols, h_tab, nullptr, 0, ga->n_nodes, sym->max_rowlen, nodes4, sym->cap_blk,
+                       sym->rowcols, sym->cols_stride);
       FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
       if (rc != -2) { ga->split_numeric = true; return rc; }
     }

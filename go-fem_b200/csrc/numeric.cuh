@@ -276,6 +276,7 @@ struct RowArgs {
 int srows_staged(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap);
 
 int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *blkcols,
-                const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4, int64_t cap_blk);
+                const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4, int64_t cap_blk,
+                const int32_t *rowcols, int cols_stride);
 
 } // namespace femb200

@@ -384,7 +384,9 @@ struct FusedTab {                       // [q][..] tables of the call (assembler
 };
 struct FusedIn {
   const double4 *nodes4;                // [n_nodes] (x, y, z, 0)
-  const int32_t *blkcols;               // ascending column nodes of row I at blkcols[blkptr[I] ...]
+  const int32_t *blkcols;               // ascending column nodes of row I at blkcols[blkptr[I] ...] (re-assembly), or
+  const int32_t *rowcols;               // at rowcols[cols_stride * n2e_ptr[I] ...] (first assembly: the pattern kernel's lists)
+  int cols_stride;
   int rl_cap;
   int64_t cap_blk;                      // capacity (node blocks) of values / blkcols: guards a call sized from a hint
   unsigned long long *guard;            // set when a row does not fit the hinted sizes (the call is then repeated)
@@ -468,7 +470,7 @@ k_srows_fused(const RowArgs a, const SRowExtra x, const FusedIn fi, const FusedT
   if (rl) {
     double X0[4] = {0.0, 0.0, 0.0, 0.0};
     if constexpr (SIMPLEX) ld256(reinterpret_cast<const double *>(fi.nodes4 + I), X0);
-    const int32_t *cols = fi.blkcols + b0;
+    const int32_t *cols = fi.rowcols ? fi.rowcols + (int64_t)fi.cols_stride * beg : fi.blkcols + b0;
     for (int p = i; p < rl; p += NDN) {
       double c4[4];
       ld256(reinterpret_cast<const double *>(fi.nodes4 + __ldg(cols + p)), c4);
@@ -806,12 +808,13 @@ static int launch_fused_T(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &
 
 // fused front end for elements with <= 4 nodes; returns -2 when it does not apply
 int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *blkcols,
-                const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4, int64_t cap_blk) {
+                const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4, int64_t cap_blk,
+                const int32_t *rowcols, int cols_stride) {
   if (sh.nn > 4) return -2;
   k_pad_nodes<<<grid_for(a.n_nodes, 256), 256, 0, ctx->stream>>>(a.n_nodes, d_nodes, nodes4);
   ctx->launches++;
   FusedIn fi;
-  fi.nodes4 = nodes4; fi.blkcols = blkcols; fi.rl_cap = 0;
+  fi.nodes4 = nodes4; fi.blkcols = blkcols; fi.rowcols = rowcols; fi.cols_stride = cols_stride; fi.rl_cap = 0;
   fi.cap_blk = cap_blk; fi.guard = (unsigned long long *)(ctx->d_scalars + 7);
   const int tpb = getenv("FEMB200_SROW_TPB") ? atoi(getenv("FEMB200_SROW_TPB")) : 32; // one warp per block: finest shared-memory granularity (measured 2-3 % over 64)
 #define FEMB_F(Dv, NNv, BK)                                                                                          \

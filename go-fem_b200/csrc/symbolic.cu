@@ -611,6 +611,7 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   // ---- node-block row pattern ----------------------------------------------------------------
   int32_t *tmpcols = nullptr;
   if ((rc = scratch_alloc(ctx, &tmpcols, ninc * nn))) return rc;
+  out->rowcols = tmpcols; out->cols_stride = nn;
   if ((rc = dev_alloc(ctx, &out->pos16, ninc * nn + 64))) return rc; // + 64: the numeric kernel stages whole 64-byte chunks of slot words
   switch (nn) {
   case 3: rc = launch_row_pattern<3>(ctx, n_nodes, out->n2e_ptr, out->n2e_t, conn32, tmpcols, rowlen, out->pos16, ga->d_node_mask); break;
@@ -702,12 +703,25 @@ int symbolic_phase(femb200_assembler *ga, const ElemShape &sh, const int32_t *co
   if (expand8) {
     const unsigned eg = grid_for(((n_nodes + 7) / 8) * 32, 256);
     unsigned long long *guard = (unsigned long long *)(ctx->d_scalars + 7);
+    // The numeric kernel of the fused path reads the row's column nodes from the pattern kernel's lists (rowcols), not from
+    // blkcols, so the expansion (120 MB of scalar indices, HBM bound) has no consumer inside the call and CAN run on the second
+    // stream beside the numeric kernel.  Measured (config 1): the step goes from 0.535 to 0.524 ms, but the numeric kernel
+    // itself stretches from 0.232 to 0.272 ms -- the two kernels share SM slots rather than overlap -- so it is opt-in
+    // (FEMB200_FORK_EXPAND=1) and the default keeps the kernels, and their roofline timings, apart.
+    cudaStream_t es = st;
+    if (ctx->stream2 && sh.nn <= 4 && getenv("FEMB200_FORK_EXPAND")) {
+      FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork2, st));
+      FEMB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork2, 0));
+      es = ctx->stream2;
+      out->expand_forked = true;
+    }
     switch (nu) {
-    case 1: k_expand8<1><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
-    case 2: k_expand8<2><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
-    default: k_expand8<3><<<eg, 256, 0, st>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
+    case 1: k_expand8<1><<<eg, 256, 0, es>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
+    case 2: k_expand8<2><<<eg, 256, 0, es>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
+    default: k_expand8<3><<<eg, 256, 0, es>>>(n_nodes, nn, out->n2e_ptr, out->blkptr, tmpcols, out->csr.indices, out->csr.indptr, ga->d_col_map, out->blkcols, out->cap_blk, guard, ctx->d_scalars); break;
     }
     ctx->launches++;
+    if (out->expand_forked) FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev_join2, ctx->stream2));
   } else {
   k_indptr<<<grid_for(ndof + 1, 256), 256, 0, st>>>(n_nodes, sh.mdpn, nu, umask, out->blkptr, out->csr.indptr);
   ctx->launches++;
