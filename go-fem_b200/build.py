@@ -18,7 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
            "-Xptxas", "-v", "-DFEMB200_BUILD"]
-CU_SOURCES = ["api.cu", "symbolic.cu", "numeric.cu", "srows.cu", "csr_ops.cu", "dist.cu", "mesh.cu"]
+CU_SOURCES = ["api.cu", "symbolic.cu", "numeric.cu", "srows.cu", "keblocks.cu", "csr_ops.cu", "dist.cu", "mesh.cu"]
 CXX_SOURCES = ["host_capi.cpp"]
 
 

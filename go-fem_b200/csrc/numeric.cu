@@ -158,10 +158,12 @@ k_numeric_rows(const NumArgs a) {
 
 // STORE = false: the reference's per-element checks only (error word), nothing is staged -- the companion of the fused
 // scalar-row kernel (srows.cu), which recomputes the geometry it needs.
-template <int D, int NN, int BKIND, bool TAB_CONST, bool STORE = true>
+// SOA: the record layout of StagSoa<NN> (numeric.cuh) for the element-block kernel instead of Stag's node-major one.
+template <int D, int NN, int BKIND, bool TAB_CONST, bool STORE = true, bool SOA = false>
 __global__ void __launch_bounds__(128, (NN <= 4 && D == 3 ? 6 : 1)) // linear tetrahedra: 75 registers, 6 blocks per SM (store bound)
 k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__restrict__ conn, double *__restrict__ stag,
-           uint8_t *__restrict__ degen, unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp) {
+           uint8_t *__restrict__ degen, unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp,
+           int64_t e_off = 0) {   // e_off: index of element 0 of this launch in the call (chunked launches; error word only)
   using B = BT<BKIND, D>;
   using S = Stag<BKIND, D, NN>;
   constexpr int NV = B::NV, REC = S::REC;
@@ -192,16 +194,36 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
   for (int q = 0; q < nqp; ++q) {
     double inv[D][D], detJ, rinv, scale;
     const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
-    double *rec = stag + (e * nqp + q) * REC;
+    constexpr int RECQ = SOA ? StagSoa<NN>::QREC : REC;
+    double *rec = stag + (e * nqp + q) * RECQ;
     if (ek) {
-      atomicMin(err, pack_error(e, q, ek));
+      atomicMin(err, pack_error(e + e_off, q, ek));
       if constexpr (STORE)
-        for (int m = 0; m < REC; ++m) rec[m] = 0.0;
+        for (int m = 0; m < RECQ; ++m) rec[m] = 0.0;
       return; // the reference stops at the first failing quadrature point of the element (:95-107)
     }
     if constexpr (!STORE) continue;
     const double f = detJ * tab.w(q) * scale; // (dJac*w)*scale, left to right (:111)
-    if constexpr (S::FIN) {
+    if constexpr (SOA) {
+      static_assert(!SOA || NV == 3, "three gradient components");
+      constexpr int NNP = StagSoa<NN>::NNP;
+      double g[3][NNP];
+#pragma unroll
+      for (int b = 0; b < NNP; ++b) {
+        if (b < NN) {
+          double vb[NV];
+          node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+          g[0][b] = vb[0]; g[1][b] = vb[NV > 1 ? 1 : 0]; g[2][b] = vb[NV > 2 ? 2 : 0];
+        } else {
+          g[0][b] = g[1][b] = g[2][b] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int v4 = 0; v4 < NNP / 4; ++v4) st256(rec + c * NNP + 4 * v4, g[c][4 * v4], g[c][4 * v4 + 1], g[c][4 * v4 + 2], g[c][4 * v4 + 3]);
+      st256(rec + 3 * NNP, f, 0.0, 0.0, 0.0);
+    } else if constexpr (S::FIN) {
 #pragma unroll
       for (int b = 0; b < NN; ++b) {
         double vb[NV];
@@ -583,6 +605,53 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
     }
   }
   if (sym->speculative) return -3; // hinted sizes are only safe with the guarded fused kernel: the caller repeats the call without hints
+  if constexpr (D == 3 && BKIND == FEMB200_B_XYZ && NN > 4) {
+    // default for Hexa8 / Tetra10 / Hexa20 solids: element blocks + ordered row gather (keblocks.cu).  The geometry is staged
+    // for one chunk of elements at a time (the chunk's records are consumed by the block kernel right behind it);
+    // FEMB200_ROWS=noderows keeps the row-centric kernel, which also takes over when the element-matrix staging does not fit.
+    const char *rows_env0 = getenv("FEMB200_ROWS");
+    const size_t ke_bytes = (size_t)n_elem * ke_doubles_per_element(NN) * sizeof(double);
+    const int64_t chunk = getenv("FEMB200_KE_CHUNK") ? atoll(getenv("FEMB200_KE_CHUNK")) : (int64_t)1 << 18;
+    const int64_t nchunk = n_elem < chunk ? (n_elem > 0 ? n_elem : 1) : chunk;
+    const size_t stag_bytes = (size_t)nchunk * sh.nqp * StagSoa<NN>::QREC * sizeof(double);
+    bool fits = (size_t)sym->max_rowlen * 9 * sizeof(double) <= ctx->smem_optin && ke_blocks_smem(NN, sh.nqp) + 1024 <= ctx->smem_optin;
+    if (fits) {
+      const size_t have = ctx->scratch.empty() ? 0 : ctx->scratch.back().size - ctx->scratch_off;
+      if (have < ke_bytes + stag_bytes + (size_t)n_elem + 1024) {
+        size_t free_b = 0, total_b = 0;
+        uint64_t reserved = 0, used = 0;
+        FEMB_CUDA_OK(ctx, cudaMemGetInfo(&free_b, &total_b));
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        const double avail = (double)free_b + (double)(reserved > used ? reserved - used : 0);
+        fits = (double)(ke_bytes + stag_bytes) < 0.85 * avail;
+      }
+    }
+    if (fits && !(rows_env0 && (!strcmp(rows_env0, "noderows") || !strcmp(rows_env0, "srow")))) {
+      double *ke = nullptr;
+      if ((rc = scratch_alloc(ctx, &ke, ke_bytes / sizeof(double)))) return rc;
+      if ((rc = scratch_alloc(ctx, &stag, stag_bytes / sizeof(double)))) return rc;
+      if ((rc = scratch_alloc(ctx, &degen, (size_t)n_elem))) return rc;
+      FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
+      for (int64_t c0 = 0; c0 < n_elem; c0 += nchunk) {
+        const int64_t nc = n_elem - c0 < nchunk ? n_elem - c0 : nchunk;
+        k_geometry<D, NN, BKIND, TAB_CONST, true, true><<<grid_for(nc, 128), 128, 0, ctx->stream>>>(nc, ga->d_nodes, conn32 + c0 * NN, stag, degen + c0, ctx->d_err,
+                                                                                                  d_tab, tl.offW, tl.offN, tl.offDN, sh.nqp, c0);
+        ctx->launches++;
+        if ((rc = ke_elem_blocks(ctx, NN, nc, stag, sh.nqp, ke + c0 * (int64_t)ke_doubles_per_element(NN), h_tab))) return rc;
+      }
+      FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
+      RowArgs a;
+      a.n_nodes = ga->n_nodes; a.n_numeric = n_elem; a.n2e_ptr = sym->n2e_ptr; a.n2e_t = sym->n2e_t; a.pos16 = sym->pos16; a.blkptr = sym->blkptr;
+      a.stag = nullptr; a.degen = degen; a.order = nullptr; a.v0 = 0; a.v1 = ga->n_nodes; a.values = sym->csr.values; a.nqp = sh.nqp; a.ninc = n_elem * NN;
+      a.has_halo = n_elem < n_elem_total ? 1 : 0;
+      for (int i = 0; i < kMaxDimC * kMaxDimC; ++i) a.C[i] = 0.0;
+      rc = ke_rows_gather(ctx, NN, a, ke, sym->max_rowlen);
+      FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
+      ga->split_numeric = true;
+      return rc;
+    }
+  }
   rc = scratch_alloc(ctx, &stag, (size_t)n_elem * sh.nqp * S::REC);
   if (rc) return rc;
   if ((rc = scratch_alloc(ctx, &degen, (size_t)n_elem))) return rc;

@@ -254,6 +254,38 @@ __device__ __forceinline__ void st256(double *p, double a, double b, double c, d
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- mbarrier + bulk (TMA 1-D) copy helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar)) : "memory");
+}
+
+// Staged geometry for the element-block kernel (keblocks.cu): per (element, point) the node gradients as three arrays
+// gx[NNP] gy[NNP] gz[NNP] (NNP = nn rounded up to 4: every array 32-byte aligned) followed by [f 0 0 0] -- in shared memory a
+// lane's two adjacent nodes are one conflict-free 128-bit load per component.
+template <int NN> struct StagSoa {
+  static constexpr int NNP = (NN + 3) & ~3;
+  static constexpr int QREC = 3 * NNP + 4;
+};
+
 struct RowArgs {
   int64_t n_nodes;
   int64_t n_numeric;          // elements [n_numeric, n_elem) are pattern-only (halo): no values
@@ -278,5 +310,11 @@ int srows_staged(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const 
 int srows_fused(femb200_ctx *ctx, const ElemShape &sh, const RowArgs &a, const double *d_nodes, const int32_t *blkcols,
                 const double *h_tab, const int32_t *order, int64_t v0, int64_t v1, int64_t rowlen_cap, double4 *nodes4, int64_t cap_blk,
                 const int32_t *rowcols, int cols_stride);
+
+// keblocks.cu: element blocks + ordered row gather for Hexa8 / Tetra10 / Hexa20 solids (XYZ filler)
+size_t ke_doubles_per_element(int nn);
+size_t ke_blocks_smem(int nn, int nqp);
+int ke_elem_blocks(femb200_ctx *ctx, int nn, int64_t n_elem, const double *stag, int nqp, double *ke, const double *C36);
+int ke_rows_gather(femb200_ctx *ctx, int nn, const RowArgs &a, const double *ke, int64_t rowlen_cap);
 
 } // namespace femb200

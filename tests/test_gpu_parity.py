@@ -830,3 +830,68 @@ def test_size_hint_of_another_mesh_is_caught_and_the_call_repeated(pkg, O):
         rp, ri, rv, ab = og.csr(with_absum=True)
         compare_csr((ip, ix, v), (rp, ri, rv), ab, TOL)
     ra.close()
+
+
+# ---- the element-block path of Hexa8 / Tetra10 / Hexa20 (csrc/keblocks.cu) ---------------------------------------------
+class _GeneralSolid:
+    """An IsoConstituter with a user-supplied 6 x 6 matrix and the XYZ strain-displacement filler."""
+
+    def __init__(self, Cm):
+        self.Cm = np.ascontiguousarray(Cm, dtype=np.float64)
+
+    def Constitutive(self):
+        return self.Cm
+
+    def BKind(self):
+        return 0
+
+
+@pytest.mark.parametrize("name,size", [("hexa8", 4), ("tetra10", 2), ("hexa20", 2)])
+@pytest.mark.parametrize("cmat", ["unsymmetric_full", "symmetric_full", "orthotropic"])
+def test_general_constitutive_matrix_on_larger_elements(pkg, O, meshes, name, size, cmat):
+    """The block kernel pulls the quadrature sum inside the contraction with C and takes short cuts for a symmetric C
+    (mirrored blocks by transposition) and for a C without normal/shear coupling (structural zeros skipped): all three
+    variants against the oracle's dense B^T C B with the same matrix."""
+    rng = np.random.default_rng(11)
+    Cm = rng.uniform(0.5, 2.0, (6, 6)) * 1e3 + np.diag([8e3] * 6)
+    if cmat == "symmetric_full":
+        Cm = 0.5 * (Cm + Cm.T)
+    elif cmat == "orthotropic":
+        Cm = 0.5 * (Cm + Cm.T)
+        Cm[:3, 3:] = 0.0
+        Cm[3:, :3] = 0.0
+        Cm[3:, 3:] = np.diag(np.diag(Cm[3:, 3:]))
+    nodes, conn = meshes.mesh_for(name, size)
+    ra = pkg.RawAssembler(nodes, 3)
+    desc = ra.make_desc(elem_of(pkg, name), _GeneralSolid(Cm))
+    assert ra.add(desc, conn=conn) == 0
+    og = O.GeneralAssembler(nodes, 7)
+    og.add_isoparametric(KINDS[name]["kind"], np.ascontiguousarray(Cm), 0, conn)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    compare_csr(ra.csr(), (rp, ri, rv), ab, TOL)
+    ra.close()
+
+
+@pytest.mark.parametrize("name", ["hexa8", "hexa20"])
+def test_collapsed_larger_elements(pkg, O, meshes, name):
+    """Bricks collapsed to wedges by REPEATING node ids (one face shrinks to an edge; a Hexa20 then names one node three
+    times): legal -- detJ stays positive at the Gauss points -- and several local nodes share a column block, so the row gather
+    adds their blocks one local node at a time, in the order of the reference's COO stream."""
+    nodes, conn0 = meshes.mesh_for(name, 3, jittered=False)
+    conn = conn0.copy()
+    for e in (4, 13):
+        X = nodes[conn0[e]]
+        ymin, xmin = X[:, 1].min(), X[:, 0].min()
+        for m in range(conn.shape[1]):
+            if abs(X[m, 1] - ymin) < 1e-9 and X[m, 0] > xmin + 1e-9:
+                tgt = [k for k in range(conn.shape[1]) if abs(X[k, 1] - ymin) < 1e-9 and abs(X[k, 2] - X[m, 2]) < 1e-9 and abs(X[k, 0] - xmin) < 1e-9][0]
+                conn[e, m] = conn0[e, tgt]
+    assert len(set(conn[4])) < conn.shape[1]
+    ga = pkg.fem.NewGeneralAssembler(nodes, 7)
+    err = ga.AddIsoparametric(elem_of(pkg, name), pkg.solids.Isotropic(1e5, 0.3).Solid3D(), len(conn), conn)
+    assert err is None, err
+    og = O.GeneralAssembler(nodes, 7)
+    Cm, bk = O.constitutive(0, 1e5, 0.3)
+    og.add_isoparametric(KINDS[name]["kind"], Cm, bk, conn)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    compare_csr(ga.Ksolid().csr(), (rp, ri, rv), ab, TOL)
