@@ -287,8 +287,9 @@ int rows_gather_W(femb200_ctx *ctx, const RowArgs &a, const double *ke, int64_t 
 
 template <int NN>
 int rows_gather_T(femb200_ctx *ctx, const RowArgs &a, const double *ke, int64_t rowlen_cap) {
-  // two warps per block while their accumulators leave room for 32 blocks per SM, else one
-  int wpb = (size_t)rowlen_cap * 9 * sizeof(double) * 2 * 32 <= 200 * 1024 ? 2 : 1;
+  // two warps per block for short rows (measured: Hexa8 1.44 -> 1.34 ms per 10^6 elements; no gain or a loss for the long rows of
+  // Tetra10 / Hexa20, whose accumulators would leave fewer resident warps)
+  int wpb = rowlen_cap <= 27 ? 2 : 1;
   if (getenv("FEMB200_GATHER_WPB")) wpb = atoi(getenv("FEMB200_GATHER_WPB"));
   if (wpb >= 4) { const int rc = rows_gather_W<NN, 4>(ctx, a, ke, rowlen_cap); if (rc != -2) return rc; }
   if (wpb >= 2) { const int rc = rows_gather_W<NN, 2>(ctx, a, ke, rowlen_cap); if (rc != -2) return rc; }
@@ -314,18 +315,21 @@ size_t ke_blocks_smem(int nn, int nqp) {
   return 0;
 }
 
-int ke_elem_blocks(femb200_ctx *ctx, int nn, int64_t n_elem, const double *stag, int nqp, double *ke, const double *C36) {
-  KeParams p;
-  p.symc = 1;
+static void make_params(const double *C36, KeParams *p, bool *ortho) {
+  p->symc = 1;
+  *ortho = true;
   for (int k = 0; k < 6; ++k)
     for (int l = 0; l < 6; ++l) {
-      p.C[k * 6 + l] = C36[k * 6 + l];
-      if (C36[k * 6 + l] != C36[l * 6 + k]) p.symc = 0;
+      p->C[k * 6 + l] = C36[k * 6 + l];
+      if (C36[k * 6 + l] != C36[l * 6 + k]) p->symc = 0;
+      if (!ortho_nonzero(k, l) && C36[k * 6 + l] != 0.0) *ortho = false;
     }
-  bool ortho = true;
-  for (int k = 0; k < 6; ++k)
-    for (int l = 0; l < 6; ++l)
-      if (!ortho_nonzero(k, l) && C36[k * 6 + l] != 0.0) ortho = false;
+}
+
+int ke_elem_blocks(femb200_ctx *ctx, int nn, int64_t n_elem, const double *stag, int nqp, double *ke, const double *C36) {
+  KeParams p;
+  bool ortho;
+  make_params(C36, &p, &ortho);
   switch (nn) {
   case 8: return ortho ? elem_blocks_T<8, true>(ctx, n_elem, stag, nqp, ke, p) : elem_blocks_T<8, false>(ctx, n_elem, stag, nqp, ke, p);
   case 10: return ortho ? elem_blocks_T<10, true>(ctx, n_elem, stag, nqp, ke, p) : elem_blocks_T<10, false>(ctx, n_elem, stag, nqp, ke, p);

@@ -607,7 +607,8 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
   if (sym->speculative) return -3; // hinted sizes are only safe with the guarded fused kernel: the caller repeats the call without hints
   if constexpr (D == 3 && BKIND == FEMB200_B_XYZ && NN > 4) {
     // default for Hexa8 / Tetra10 / Hexa20 solids: element blocks + ordered row gather (keblocks.cu).  The geometry is staged
-    // for one chunk of elements at a time (the chunk's records are consumed by the block kernel right behind it);
+    // for one chunk of elements at a time (the chunk's records are consumed by the block kernel right behind it; computing
+    // the geometry inside the block kernel was measured: 27 of 64 threads busy on long dependent chains, 1.7x slower).
     // FEMB200_ROWS=noderows keeps the row-centric kernel, which also takes over when the element-matrix staging does not fit.
     const char *rows_env0 = getenv("FEMB200_ROWS");
     const size_t ke_bytes = (size_t)n_elem * ke_doubles_per_element(NN) * sizeof(double);
