@@ -173,6 +173,22 @@ template <class T> inline int scratch_alloc(femb200_ctx *ctx, T **p, size_t n) {
   ctx->scratch_used += bytes;
   return 0;
 }
+// bytes of NEW device memory the arena would have to reserve for the given requests, in order (mirrors scratch_alloc)
+inline size_t scratch_extra_needed(const femb200_ctx *ctx, const size_t *bytes_each, int n) {
+  size_t cap = ctx->scratch.empty() ? 0 : ctx->scratch.back().size, off = ctx->scratch.empty() ? 0 : ctx->scratch_off, extra = 0;
+  bool empty = ctx->scratch.empty();
+  for (int i = 0; i < n; ++i) {
+    const size_t bytes = ((bytes_each[i] ? bytes_each[i] : 1) + 255) & ~(size_t)255;
+    if (empty || off + bytes > cap) {
+      size_t sz = bytes > ctx->scratch_hint ? bytes : ctx->scratch_hint;
+      if (!empty && sz < cap / 2) sz = cap / 2;
+      extra += sz;
+      cap = sz; off = 0; empty = false;
+    }
+    off += bytes;
+  }
+  return extra;
+}
 inline void scratch_release(femb200_ctx *ctx, bool drop_all = false) {
   if (ctx->scratch.size() > 1 || drop_all) { // consolidate: the next call gets one chunk that fits everything
     for (auto &c : ctx->scratch) cudaFreeAsync(c.p, ctx->stream);

@@ -617,22 +617,25 @@ static int launch_dof_T(femb200_assembler *ga, const ElemShape &sh, const double
     const size_t stag_bytes = (size_t)nchunk * sh.nqp * StagSoa<NN>::QREC * sizeof(double);
     bool fits = (size_t)sym->max_rowlen * 9 * sizeof(double) <= ctx->smem_optin && ke_blocks_smem(NN, sh.nqp) + 1024 <= ctx->smem_optin;
     if (fits) {
-      const size_t have = ctx->scratch.empty() ? 0 : ctx->scratch.back().size - ctx->scratch_off;
-      if (have < ke_bytes + stag_bytes + (size_t)n_elem + 1024) {
+      const size_t req[3] = {stag_bytes, (size_t)n_elem, ke_bytes};             // the order of the allocations below
+      const size_t extra = scratch_extra_needed(ctx, req, 3);
+      if (extra) {
         size_t free_b = 0, total_b = 0;
         uint64_t reserved = 0, used = 0;
         FEMB_CUDA_OK(ctx, cudaMemGetInfo(&free_b, &total_b));
         cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
         cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
         const double avail = (double)free_b + (double)(reserved > used ? reserved - used : 0);
-        fits = (double)(ke_bytes + stag_bytes) < 0.85 * avail;
+        fits = (double)extra < 0.85 * avail;
       }
     }
     if (fits && !(rows_env0 && (!strcmp(rows_env0, "noderows") || !strcmp(rows_env0, "srow")))) {
       double *ke = nullptr;
-      if ((rc = scratch_alloc(ctx, &ke, ke_bytes / sizeof(double)))) return rc;
+      // the small arrays first: a new arena chunk is at least half the size of the previous one, so a request that FOLLOWS the
+      // element-matrix staging (tens of GB) would reserve half as much again
       if ((rc = scratch_alloc(ctx, &stag, stag_bytes / sizeof(double)))) return rc;
       if ((rc = scratch_alloc(ctx, &degen, (size_t)n_elem))) return rc;
+      if ((rc = scratch_alloc(ctx, &ke, ke_bytes / sizeof(double)))) return rc;
       FEMB_CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
       for (int64_t c0 = 0; c0 < n_elem; c0 += nchunk) {
         const int64_t nc = n_elem - c0 < nchunk ? n_elem - c0 : nchunk;

@@ -47,7 +47,8 @@ def launches(src, dst, cmd=""):
 
 
 def full(src, dst, note=""):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # src: a .ncu-rep, or the CSV of `ncu -i rep --page raw --csv` exported on the GPU box (reports over 64 MB do not travel)
+    out = open(src).read() if src.endswith(".csv") else subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     u = dict(zip(hdr, units))
