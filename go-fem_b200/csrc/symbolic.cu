@@ -288,6 +288,9 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   __syncwarp(gmask);
 
   // 4. compact the distinct keys, rank them
+  // large, mostly empty tables (Tetra10: 20-65 of 128 slots): rank the compacted list, not every slot.  Measured: Tetra10 row
+  // pattern 1.21 -> 1.03 ms per 748,800 elements; Hexa20 (50-81 of 128 slots) 2 % slower, Hexa8 equal: not used there.
+  constexpr bool RANK_COMPACT = (HS / G > 4) && (NN * 8 < HS);
   int cnt = 0;
 #pragma unroll
   for (int s = 0; s < HS / G; ++s) {
@@ -296,6 +299,7 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
     const unsigned bal = (__ballot_sync(gmask, has) >> gshift) & 0xffu;
     const int off = cnt + __popc(bal & ((1u << l) - 1u));
     if (has && off < CAP) ul[off] = key;
+    if constexpr (RANK_COMPACT) rk[s * G + l] = has ? off : 0;   // slot -> position in the compacted list (rank follows below)
     cnt += __popc(bal);
   }
   ovf = __any_sync(gmask, ovf) || cnt > CAP;
@@ -303,7 +307,44 @@ k_row_pattern_group(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr, uint32
   if (l < 4 && cnt + l < CAP + 4) ul[cnt + l] = 0x7fffffff;       // padding for the four-wide rank loop (ul holds CAP + 4 words)
   __syncwarp(gmask);
   int32_t *gcols = tmpcols + (int64_t)NN * beg;
-  {
+  if constexpr (RANK_COMPACT) {
+    // lane l ranks the compacted keys l, l+8, ... (four at a time against the whole list): cnt/8 keys per lane instead of
+    // the HS/8 slots of the table
+    constexpr int NCH = (CAP + 4 * G - 1) / (4 * G);
+    int rr[NCH][4];
+    int32_t key[NCH][4];
+    const int4 *u4 = reinterpret_cast<const int4 *>(ul);
+    const int nj = (cnt + 3) / 4;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { rr[c][i] = 0; key[c][i] = 0x7fffffff; }
+      if (c * 4 * G < cnt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int x = c * 4 * G + l + G * i;
+          if (x < cnt) key[c][i] = ul[x];
+        }
+        for (int j = 0; j < nj; ++j) {
+          const int4 w = u4[j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rr[c][i] += (w.x < key[c][i]) + (w.y < key[c][i]) + (w.z < key[c][i]) + (w.w < key[c][i]);
+        }
+      }
+    }
+    __syncwarp(gmask);                                             // every lane has read the keys: the list now takes the ranks
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = c * 4 * G + l + G * i;
+        if (x < cnt) { ul[x] = rr[c][i]; gcols[rr[c][i]] = key[c][i]; }
+      }
+    __syncwarp(gmask);
+#pragma unroll
+    for (int s = 0; s < HS / G; ++s)
+      if (keys[s * G + l] >= 0) rk[s * G + l] = ul[rk[s * G + l]];
+  } else {
     int32_t key[HS / G];
     int rr[HS / G];
 #pragma unroll
