@@ -100,8 +100,9 @@ k_numeric_rows(const NumArgs a) {
     }
     bool bad = false;
     for (int q = 0; q < a.nqp; ++q) {
-      double inv[D][D], detJ, rinv, scale;
-      const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
+      LuFac<D> fac;
+      double detJ, rinv, scale;
+      const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, fac, detJ, rinv, scale);
       if (ek) {
         atomicMin(a.err, pack_error(e, q, ek));
         bad = true;
@@ -109,12 +110,12 @@ k_numeric_rows(const NumArgs a) {
       }
       const double f = detJ * tab.w(q) * scale; // (dJac*w)*scale, left to right (:111)
       double va[NV], E[NDN][B::DIMC];
-      node_vals<BKIND, D, NN>(tab, q, la, inv, rinv, va);
+      node_vals<BKIND, D, NN>(tab, q, la, fac, rinv, va);
       bt_c<BKIND, D>(tab, va, f, E);
 #pragma unroll
       for (int b = 0; b < NN; ++b) {
         double vb[NV], blk[NB2];
-        node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+        node_vals<BKIND, D, NN>(tab, q, b, fac, rinv, vb);
         e_b<BKIND, D>(E, vb, blk);
         if constexpr (ACC_REGS) {
 #pragma unroll
@@ -160,7 +161,7 @@ k_numeric_rows(const NumArgs a) {
 // scalar-row kernel (srows.cu), which recomputes the geometry it needs.
 // SOA: the record layout of StagSoa<NN> (numeric.cuh) for the element-block kernel instead of Stag's node-major one.
 template <int D, int NN, int BKIND, bool TAB_CONST, bool STORE = true, bool SOA = false>
-__global__ void __launch_bounds__(128, (NN <= 4 && D == 3 ? 6 : 1)) // linear tetrahedra: 75 registers, 6 blocks per SM (store bound)
+__global__ void __launch_bounds__(128, (NN <= 4 && D == 3 ? (STORE ? 4 : 6) : 1)) // linear tetrahedra: checks only 6 blocks per SM, staging (opt-in path) 4
 k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__restrict__ conn, double *__restrict__ stag,
            uint8_t *__restrict__ degen, unsigned long long *err, const double *tab_g, int offW, int offN, int offDN, int nqp,
            int64_t e_off = 0) {   // e_off: index of element 0 of this launch in the call (chunked launches; error word only)
@@ -192,8 +193,9 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
   }
   if constexpr (STORE) degen[e] = dup ? 1 : 0;
   for (int q = 0; q < nqp; ++q) {
-    double inv[D][D], detJ, rinv, scale;
-    const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
+    LuFac<D> fac;
+      double detJ, rinv, scale;
+    const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, fac, detJ, rinv, scale);
     constexpr int RECQ = SOA ? StagSoa<NN>::QREC : REC;
     double *rec = stag + (e * nqp + q) * RECQ;
     if (ek) {
@@ -207,27 +209,29 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
     if constexpr (SOA) {
       static_assert(!SOA || NV == 3, "three gradient components");
       constexpr int NNP = StagSoa<NN>::NNP;
-      double g[3][NNP];
 #pragma unroll
-      for (int b = 0; b < NNP; ++b) {
-        if (b < NN) {
-          double vb[NV];
-          node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
-          g[0][b] = vb[0]; g[1][b] = vb[NV > 1 ? 1 : 0]; g[2][b] = vb[NV > 2 ? 2 : 0];
-        } else {
-          g[0][b] = g[1][b] = g[2][b] = 0.0;
+      for (int v4 = 0; v4 < NNP / 4; ++v4) {                // four nodes at a time: one 256-bit store per component
+        double g[3][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int b = 4 * v4 + k;
+          if (b < NN) {
+            double vb[NV];
+            node_vals<BKIND, D, NN>(tab, q, b, fac, rinv, vb);
+            g[0][k] = vb[0]; g[1][k] = vb[NV > 1 ? 1 : 0]; g[2][k] = vb[NV > 2 ? 2 : 0];
+          } else {
+            g[0][k] = g[1][k] = g[2][k] = 0.0;
+          }
         }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) st256(rec + c * NNP + 4 * v4, g[c][0], g[c][1], g[c][2], g[c][3]);
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int v4 = 0; v4 < NNP / 4; ++v4) st256(rec + c * NNP + 4 * v4, g[c][4 * v4], g[c][4 * v4 + 1], g[c][4 * v4 + 2], g[c][4 * v4 + 3]);
       st256(rec + 3 * NNP, f, 0.0, 0.0, 0.0);
     } else if constexpr (S::FIN) {
 #pragma unroll
       for (int b = 0; b < NN; ++b) {
         double vb[NV];
-        node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+        node_vals<BKIND, D, NN>(tab, q, b, fac, rinv, vb);
         st256(rec + 4 * b, vb[0], vb[1], vb[2], f);
       }
     } else {
@@ -235,7 +239,7 @@ k_geometry(int64_t n_elem, const double *__restrict__ nodes, const int32_t *__re
 #pragma unroll
       for (int b = 0; b < NN; ++b) {
         double vb[NV];
-        node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+        node_vals<BKIND, D, NN>(tab, q, b, fac, rinv, vb);
 #pragma unroll
         for (int v = 0; v < NV; ++v) rv[b * NV + v] = vb[v];
       }
@@ -887,8 +891,9 @@ __global__ void k_strains(int64_t n_elem, const double *__restrict__ nodes, cons
     for (int j = 0; j < D; ++j) X[b][j] = nodes[nd[b] * 3 + j];
   }
   for (int q = 0; q < nqp; ++q) {
-    double inv[D][D], detJ, rinv, scale;
-    const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, inv, detJ, rinv, scale);
+    LuFac<D> fac;
+      double detJ, rinv, scale;
+    const int ek = qp_geometry<D, NN, B::RADIAL>(tab, q, X, fac, detJ, rinv, scale);
     if (ek) { atomicMin(err, pack_error(e, q, ek)); return; }
     double s[DIMC];
 #pragma unroll
@@ -896,7 +901,7 @@ __global__ void k_strains(int64_t n_elem, const double *__restrict__ nodes, cons
 #pragma unroll
     for (int b = 0; b < NN; ++b) {
       double vb[NV];
-      node_vals<BKIND, D, NN>(tab, q, b, inv, rinv, vb);
+      node_vals<BKIND, D, NN>(tab, q, b, fac, rinv, vb);
 #pragma unroll
       for (int i = 0; i < NDN; ++i) {
         const double ui = u[nd[b] * mdpn + dofmap[i]];

@@ -65,8 +65,16 @@ template <bool TAB_CONST> struct Tab {
 // Jacobians (collapsed elements: two identical rows) give EXACTLY 0 -> "zero determinant", and the
 // sign of a degenerate element is not decided by FMA rounding noise.  The inverse is the adjugate
 // scaled by 1/det (differences to the reference's LU solve are O(eps * cond)).
-template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D][D]) {
-  double A[D][D];
+// LuFac: the factors of that LU (unit lower multipliers below the diagonal, U on and above), the row interchanges and the
+// reciprocals of the pivots -- what gonum's Dense.Solve (Dgetrf + Dgetrs) works with.
+template <int D> struct LuFac {
+  double a[D][D];
+  double rdiag[D];
+  int p[D];
+};
+
+template <int D> __device__ __forceinline__ double lu_factor(const double (&Jin)[D][D], LuFac<D> &f) {
+  double (&A)[D][D] = f.a;
 #pragma unroll
   for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -82,6 +90,7 @@ template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D]
       const double v = fabs(A[i][j]);
       if (v > best) { best = v; p = i; }
     }
+    f.p[j] = p;
 #pragma unroll
     for (int i = j + 1; i < D; ++i)
       if (p == i) {
@@ -91,11 +100,13 @@ template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D]
       }
     const double piv = A[j][j];
     det = __dmul_rn(det, piv);
+    f.rdiag[j] = 1.0 / piv;
     if (piv != 0.0) {
-      const double r = 1.0 / piv;
+      const double r = f.rdiag[j];
 #pragma unroll
       for (int i = j + 1; i < D; ++i) {
         const double l = __dmul_rn(A[i][j], r);
+        A[i][j] = l;
 #pragma unroll
         for (int k = j + 1; k < D; ++k) A[i][k] = __dsub_rn(A[i][k], __dmul_rn(l, A[j][k])); // no FMA: same rounding as the reference's LU
       }
@@ -104,20 +115,58 @@ template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D]
   return det;
 }
 
-template <int D> __device__ __forceinline__ double inv_det(const double (&J)[D][D], double (&inv)[D][D]);
-template <> __device__ __forceinline__ double inv_det<1>(const double (&J)[1][1], double (&inv)[1][1]) {
-  inv[0][0] = 1.0 / J[0][0];
-  return J[0][0];
+template <int D> __device__ __forceinline__ double lu_det(const double (&Jin)[D][D]) {
+  LuFac<D> f;
+  return lu_factor<D>(Jin, f);
 }
-template <> __device__ __forceinline__ double inv_det<2>(const double (&J)[2][2], double (&inv)[2][2]) {
-  const double det = lu_det<2>(J);
+
+// x <- J^-1 x with the factors above, operation by operation as Dgetrs does it (row interchanges, unit-lower forward
+// substitution, upper backward substitution with a multiplication by the reciprocal pivot; no FMA):
+// dNxy.Solve(jac, dN) of assembler_isoparametric.go:100 column by column.  An adjugate inverse differs from this by
+// O(eps*cond) of the LARGEST term -- 1e-10 relative on gradient components that nearly cancel (measured on the Tetra10
+// benchmark mesh), which showed up as 9.6e-13 normalised error in K; with the same operations the gradients agree.
+template <int D> __device__ __forceinline__ void lu_solve(const LuFac<D> &f, double (&x)[D]);
+template <> __device__ __forceinline__ void lu_solve<1>(const LuFac<1> &f, double (&x)[1]) { x[0] = __dmul_rn(x[0], f.rdiag[0]); }
+template <> __device__ __forceinline__ void lu_solve<2>(const LuFac<2> &f, double (&x)[2]) {
+  const bool s01 = f.p[0] == 1;
+  double x0 = s01 ? x[1] : x[0], x1 = s01 ? x[0] : x[1];
+  x1 = __dsub_rn(x1, __dmul_rn(f.a[1][0], x0));            // (Dtrsm skips zero multipliers: the same value up to the sign of a zero)
+  x1 = __dmul_rn(x1, f.rdiag[1]);
+  x0 = __dsub_rn(x0, __dmul_rn(f.a[0][1], x1));
+  x0 = __dmul_rn(x0, f.rdiag[0]);
+  x[0] = x0; x[1] = x1;
+}
+template <> __device__ __forceinline__ void lu_solve<3>(const LuFac<3> &f, double (&x)[3]) {
+  // scalars and selects only: an indexed swap of x[] sent the vector to local memory
+  const bool s01 = f.p[0] == 1, s02 = f.p[0] == 2, s12 = f.p[1] == 2;
+  const double y0 = s01 ? x[1] : (s02 ? x[2] : x[0]);      // rows 0 <-> p[0]
+  const double y1 = s01 ? x[0] : x[1], y2 = s02 ? x[0] : x[2];
+  double x0 = y0, x1 = s12 ? y2 : y1, x2 = s12 ? y1 : y2;  // rows 1 <-> p[1]
+  x1 = __dsub_rn(x1, __dmul_rn(f.a[1][0], x0));            // (Dtrsm skips zero multipliers: the same value up to the sign of a zero)
+  x2 = __dsub_rn(x2, __dmul_rn(f.a[2][0], x0));
+  x2 = __dsub_rn(x2, __dmul_rn(f.a[2][1], x1));
+  x2 = __dmul_rn(x2, f.rdiag[2]);
+  x1 = __dsub_rn(x1, __dmul_rn(f.a[1][2], x2));
+  x1 = __dmul_rn(x1, f.rdiag[1]);
+  x0 = __dsub_rn(x0, __dmul_rn(f.a[0][1], x1));
+  x0 = __dsub_rn(x0, __dmul_rn(f.a[0][2], x2));
+  x0 = __dmul_rn(x0, f.rdiag[0]);
+  x[0] = x0; x[1] = x1; x[2] = x2;
+}
+
+// adjugate inverse scaled by 1/det (only for the condition check and the Strains helper: O(eps*cond) off the LU solve)
+template <int D> __device__ __forceinline__ double inv_det(const double (&J)[D][D], double (&inv)[D][D], double det);
+template <> __device__ __forceinline__ double inv_det<1>(const double (&J)[1][1], double (&inv)[1][1], double det) {
+  inv[0][0] = 1.0 / J[0][0];
+  return det;
+}
+template <> __device__ __forceinline__ double inv_det<2>(const double (&J)[2][2], double (&inv)[2][2], double det) {
   const double r = 1.0 / det;
   inv[0][0] = J[1][1] * r; inv[0][1] = -J[0][1] * r;
   inv[1][0] = -J[1][0] * r; inv[1][1] = J[0][0] * r;
   return det;
 }
-template <> __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&inv)[3][3]) {
-  const double det = lu_det<3>(J);
+template <> __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&inv)[3][3], double det) {
   const double r = 1.0 / det;
   inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * r;
   inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * r;
@@ -145,7 +194,7 @@ template <int D> __device__ __forceinline__ double norm1(const double (&A)[D][D]
 // Geometry of one quadrature point.  Returns the error kind (0 = ok) exactly where the reference
 // would have returned it (assembler_isoparametric.go:95-107).
 template <int D, int NN, bool RADIAL, class TabT>
-__device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double (&X)[NN][D], double (&inv)[D][D],
+__device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double (&X)[NN][D], LuFac<D> &fac,
                                            double &detJ, double &rinv, double &scale) {
   double J[D][D];
 #pragma unroll
@@ -160,10 +209,14 @@ __device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double 
 #pragma unroll
       for (int j = 0; j < D; ++j) J[i][j] = __dadd_rn(J[i][j], __dmul_rn(dn, X[b][j])); // jac.Mul(dN, X): node-ascending, unfused (:93)
     }
-  detJ = inv_det<D>(J, inv);
+  detJ = lu_factor<D>(J, fac);
   if (detJ < 0) return FEMB200_ERR_NEG_DET;
   if (detJ < 1e-12) return FEMB200_ERR_ZERO_DET;
-  if (norm1<D>(J) * norm1<D>(inv) > 1e16) return FEMB200_ERR_SOLVE;
+  {
+    double inv[D][D];
+    inv_det<D>(J, inv, detJ);
+    if (norm1<D>(J) * norm1<D>(inv) > 1e16) return FEMB200_ERR_SOLVE;
+  }
   scale = 1.0;
   rinv = 0.0;
   if constexpr (RADIAL) {
@@ -179,16 +232,12 @@ __device__ __forceinline__ int qp_geometry(const TabT &tab, int q, const double 
 
 // v[] of one node at quadrature point q (see BT above)
 template <int BKIND, int D, int NN, class TabT>
-__device__ __forceinline__ void node_vals(const TabT &tab, int q, int b, const double (&inv)[D][D], double rinv,
+__device__ __forceinline__ void node_vals(const TabT &tab, int q, int b, const LuFac<D> &fac, double rinv,
                                           double (&v)[BT<BKIND, D>::NV]) {
   double g[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) s = fma(inv[i][j], tab.template dN<D, NN>(q, j, b), s);
-    g[i] = s;
-  }
+  for (int i = 0; i < D; ++i) g[i] = tab.template dN<D, NN>(q, i, b);
+  lu_solve<D>(fac, g);                                      // column b of dNxy.Solve(jac, dN) (:100)
   if constexpr (BKIND == FEMB200_B_AXISYM) {
     v[0] = g[0]; v[1] = g[1]; v[2] = tab.template N<NN>(q, b) * rinv;
   } else if constexpr (BKIND == FEMB200_B_THERMAL_AXISYM) {

@@ -220,22 +220,52 @@ struct Tetra10 : IsoBase {
   std::vector<r3::Vec> IsoparametricNodes() const override {
     return {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {.5, 0, 0}, {0, .5, 0}, {0, 0, .5}, {.5, .5, 0}, {0, .5, .5}, {.5, 0, .5}};
   }
-  static constexpr int edge[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {2, 3}, {1, 3}};
-  std::vector<double> Basis(r3::Vec v) const override {
-    const double L[4] = {1 - v.X - v.Y - v.Z, v.X, v.Y, v.Z};
+  std::vector<double> Basis(r3::Vec v) const override { // tetra10.go:45-58: the reference's expansion, term by term (same rounding)
     std::vector<double> N(10);
-    for (int i = 0; i < 4; ++i) N[i] = L[i] * (2 * L[i] - 1);
-    for (int k = 0; k < 6; ++k) N[4 + k] = 4 * L[edge[k][0]] * L[edge[k][1]];
+    const double X = v.X, Y = v.Y, Z = v.Z;
+    N[0] = 2*X*X + 4*X*Y + 4*X*Z - 3*X + 2*Y*Y + 4*Y*Z - 3*Y + 2*Z*Z - 3*Z + 1;
+    N[1] = 2*X*X - X;
+    N[2] = 2*Y*Y - Y;
+    N[3] = 2*Z*Z - Z;
+    N[4] = 4*X - 4*X*Y - 4*X*Z - 4*X*X;
+    N[5] = 4*Y - 4*X*Y - 4*Y*Z - 4*Y*Y;
+    N[6] = 4*Z - 4*X*Z - 4*Y*Z - 4*Z*Z;
+    N[7] = 4 * X * Y;
+    N[8] = 4 * Y * Z;
+    N[9] = 4 * X * Z;
     return N;
   }
-  std::vector<double> BasisDiff(r3::Vec v) const override {
-    const double L[4] = {1 - v.X - v.Y - v.Z, v.X, v.Y, v.Z};
-    const double dL[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  std::vector<double> BasisDiff(r3::Vec v) const override { // tetra10.go:60-96: the reference's expansion, term by term (same rounding)
     std::vector<double> d(30);
-    for (int c = 0; c < 3; ++c) {
-      for (int i = 0; i < 4; ++i) d[c * 10 + i] = (4 * L[i] - 1) * dL[i][c];
-      for (int k = 0; k < 6; ++k) d[c * 10 + 4 + k] = 4 * (dL[edge[k][0]][c] * L[edge[k][1]] + L[edge[k][0]] * dL[edge[k][1]][c]);
-    }
+    const double X = v.X, Y = v.Y, Z = v.Z;
+    d[0] = 4*X + 4*Y + 4*Z - 3;
+    d[1] = 4*X - 1;
+    d[2] = 0; d[3] = 0;
+    d[4] = 4 - 4*Y - 4*Z - 8*X;
+    d[5] = -4 * Y;
+    d[6] = -4 * Z;
+    d[7] = 4 * Y;
+    d[8] = 0;
+    d[9] = 4 * Z;
+    d[10] = 4*X + 4*Y + 4*Z - 3;
+    d[11] = 0;
+    d[12] = 4*Y - 1;
+    d[13] = 0;
+    d[14] = -4 * X;
+    d[15] = 4 - 8*Y - 4*Z - 4*X;
+    d[16] = -4 * Z;
+    d[17] = 4 * X;
+    d[18] = 4 * Z;
+    d[19] = 0;
+    d[20] = 4*X + 4*Y + 4*Z - 3;
+    d[21] = 0; d[22] = 0;
+    d[23] = 4*Z - 1;
+    d[24] = -4 * X;
+    d[25] = -4 * Y;
+    d[26] = 4 - 4*Y - 8*Z - 4*X;
+    d[27] = 0;
+    d[28] = 4 * Y;
+    d[29] = 4 * X;
     return d;
   }
   void Quadrature(std::vector<r3::Vec> &p, std::vector<double> &w) const override { // tetra10.go:98-112, weights 1/4 (8-Q1)
@@ -252,17 +282,46 @@ struct Hexa8 : IsoBase {
   int LenNodes() const override { return 8; }
   fem::DofsFlag Dofs() const override { return NodeDofs ? NodeDofs : fem::DofPos; }
   std::vector<r3::Vec> IsoparametricNodes() const override { std::vector<r3::Vec> n; for (auto &p : P) n.push_back({p[0], p[1], p[2]}); return n; }
-  std::vector<double> Basis(r3::Vec v) const override {
+  std::vector<double> Basis(r3::Vec v) const override { // hexa8.go:46-57: the reference's expansion, term by term (same rounding)
     std::vector<double> N(8);
-    for (int a = 0; a < 8; ++a) N[a] = (1 + v.X * P[a][0]) * (1 + v.Y * P[a][1]) * (1 + v.Z * P[a][2]) / 8;
+    const double X = v.X, Y = v.Y, Z = v.Z;
+    N[0] = (Z*Y - Y - X - Z + Z*X + Y*X - Z*Y*X + 1) / 8;
+    N[1] = (X - Y - Z + Z*Y - Z*X - Y*X + Z*Y*X + 1) / 8;
+    N[2] = (Y - Z + X - Z*Y - Z*X + Y*X - Z*Y*X + 1) / 8;
+    N[3] = (Y - Z - X - Z*Y + Z*X - Y*X + Z*Y*X + 1) / 8;
+    N[4] = (Z - Y - X - Z*Y - Z*X + Y*X + Z*Y*X + 1) / 8;
+    N[5] = (Z - Y + X - Z*Y + Z*X - Y*X - Z*Y*X + 1) / 8;
+    N[6] = (Z + Y + X + Z*Y + Z*X + Y*X + Z*Y*X + 1) / 8;
+    N[7] = (Z + Y - X + Z*Y - Z*X - Y*X - Z*Y*X + 1) / 8;
     return N;
   }
-  std::vector<double> BasisDiff(r3::Vec v) const override {
+  std::vector<double> BasisDiff(r3::Vec v) const override { // hexa8.go:67-96: the reference's expansion, term by term (same rounding)
     std::vector<double> d(24);
-    for (int a = 0; a < 8; ++a) {
-      const double fx = 1 + v.X * P[a][0], fy = 1 + v.Y * P[a][1], fz = 1 + v.Z * P[a][2];
-      d[a] = P[a][0] * fy * fz / 8; d[8 + a] = fx * P[a][1] * fz / 8; d[16 + a] = fx * fy * P[a][2] / 8;
-    }
+    const double X = v.X, Y = v.Y, Z = v.Z;
+    d[0] = (Z + Y - (Z * Y) - 1) / 8;
+    d[1] = ((Z * Y) - Y - Z + 1) / 8;
+    d[2] = (Y - Z - (Z * Y) + 1) / 8;
+    d[3] = (Z - Y + (Z * Y) - 1) / 8;
+    d[4] = (Y - Z + (Z * Y) - 1) / 8;
+    d[5] = (Z - Y - (Z * Y) + 1) / 8;
+    d[6] = (Z + Y + (Z * Y) + 1) / 8;
+    d[7] = (-Z - Y - (Z * Y) - 1) / 8;
+    d[8] = (Z + X - (Z * X) - 1) / 8;
+    d[9] = (Z - X + (Z * X) - 1) / 8;
+    d[10] = (X - Z - (Z * X) + 1) / 8;
+    d[11] = ((Z * X) - X - Z + 1) / 8;
+    d[12] = (X - Z + (Z * X) - 1) / 8;
+    d[13] = (-Z - X - (Z * X) - 1) / 8;
+    d[14] = (Z + X + (Z * X) + 1) / 8;
+    d[15] = (Z - X - (Z * X) + 1) / 8;
+    d[16] = (Y + X - (Y * X) - 1) / 8;
+    d[17] = (Y - X + (Y * X) - 1) / 8;
+    d[18] = (-Y - X - (Y * X) - 1) / 8;
+    d[19] = (X - Y + (Y * X) - 1) / 8;
+    d[20] = ((Y * X) - X - Y + 1) / 8;
+    d[21] = (X - Y - (Y * X) + 1) / 8;
+    d[22] = (Y + X + (Y * X) + 1) / 8;
+    d[23] = (Y - X - (Y * X) + 1) / 8;
     return d;
   }
   void Quadrature(std::vector<r3::Vec> &p, std::vector<double> &w) const override { // hexa8.go:98-108
@@ -280,37 +339,96 @@ struct Hexa20 : IsoBase {
   int LenNodes() const override { return 20; }
   fem::DofsFlag Dofs() const override { return NodeDofs ? NodeDofs : fem::DofPos; }
   std::vector<r3::Vec> IsoparametricNodes() const override { std::vector<r3::Vec> n; for (auto &p : P) n.push_back({p[0], p[1], p[2]}); return n; }
-  // value and gradient of node a at (x,y,z); serendipity: corners (1+xx_a)(1+yy_a)(1+zz_a)(xx_a+yy_a+zz_a-2)/8,
-  // mid-edge on the axis with coordinate 0: (1-x^2)(1+yy_a)(1+zz_a)/4 (cyclic)
-  static void eval(int a, const double c[3], double &N, double g[3]) {
-    const double *p = P[a];
-    int zero = -1;
-    for (int k = 0; k < 3; ++k) if (p[k] == 0) zero = k;
-    if (zero < 0) {
-      const double f[3] = {1 + c[0] * p[0], 1 + c[1] * p[1], 1 + c[2] * p[2]};
-      const double s = c[0] * p[0] + c[1] * p[1] + c[2] * p[2] - 2;
-      N = f[0] * f[1] * f[2] * s / 8;
-      for (int k = 0; k < 3; ++k) {
-        const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-        g[k] = p[k] * f[k1] * f[k2] * (s + f[k]) / 8;
-      }
-    } else {
-      const int k1 = (zero + 1) % 3, k2 = (zero + 2) % 3;
-      const double q = 1 - c[zero] * c[zero], f1 = 1 + c[k1] * p[k1], f2 = 1 + c[k2] * p[k2];
-      N = q * f1 * f2 / 4;
-      g[zero] = -2 * c[zero] * f1 * f2 / 4;
-      g[k1] = q * p[k1] * f2 / 4;
-      g[k2] = q * f1 * p[k2] / 4;
-    }
-  }
-  std::vector<double> Basis(r3::Vec v) const override {
-    std::vector<double> N(20); const double c[3] = {v.X, v.Y, v.Z}; double g[3];
-    for (int a = 0; a < 20; ++a) eval(a, c, N[a], g);
+  std::vector<double> Basis(r3::Vec v) const override { // hexa20.go:59-86: the reference's expansion, term by term (same rounding)
+    std::vector<double> N(20);
+    const double X = v.X, Y = v.Y, Z = v.Z;
+    double x2 = X * X, y2 = Y * Y, z2 = Z * Z;
+    N[0] = ((Y - 1) * (X - 1) * (Z - 1) * (Y + X + Z + 2)) / 8;
+    N[1] = -((Y + 1) * (X - 1) * (Z - 1) * (X - Y + Z + 2)) / 8;
+    N[2] = -((Y + 1) * (X + 1) * (Z - 1) * (Y + X - Z - 2)) / 8;
+    N[3] = -((Y - 1) * (X + 1) * (Z - 1) * (Y - X + Z + 2)) / 8;
+    N[4] = -((Y - 1) * (X - 1) * (Z + 1) * (Y + X - Z + 2)) / 8;
+    N[5] = -((Y + 1) * (X - 1) * (Z + 1) * (Y - X + Z - 2)) / 8;
+    N[6] = ((Y + 1) * (X + 1) * (Z + 1) * (Y + X + Z - 2)) / 8;
+    N[7] = ((Y - 1) * (X + 1) * (Z + 1) * (Y - X - Z + 2)) / 8;
+    N[8] = -((y2 - 1) * (X - 1) * (Z - 1)) / 4;
+    N[9] = ((x2 - 1) * (Y + 1) * (Z - 1)) / 4;
+    N[10] = ((y2 - 1) * (X + 1) * (Z - 1)) / 4;
+    N[11] = -((x2 - 1) * (Y - 1) * (Z - 1)) / 4;
+    N[12] = ((y2 - 1) * (X - 1) * (Z + 1)) / 4;
+    N[13] = -((x2 - 1) * (Y + 1) * (Z + 1)) / 4;
+    N[14] = -((y2 - 1) * (X + 1) * (Z + 1)) / 4;
+    N[15] = ((x2 - 1) * (Y - 1) * (Z + 1)) / 4;
+    N[16] = -((z2 - 1) * (Y - 1) * (X - 1)) / 4;
+    N[17] = ((z2 - 1) * (Y + 1) * (X - 1)) / 4;
+    N[18] = -((z2 - 1) * (Y + 1) * (X + 1)) / 4;
+    N[19] = ((z2 - 1) * (Y - 1) * (X + 1)) / 4;
     return N;
   }
-  std::vector<double> BasisDiff(r3::Vec v) const override {
-    std::vector<double> d(60); const double c[3] = {v.X, v.Y, v.Z}; double N, g[3];
-    for (int a = 0; a < 20; ++a) { eval(a, c, N, g); d[a] = g[0]; d[20 + a] = g[1]; d[40 + a] = g[2]; }
+  std::vector<double> BasisDiff(r3::Vec v) const override { // hexa20.go:96-163: the reference's expansion, term by term (same rounding)
+    std::vector<double> d(60);
+    const double X = v.X, Y = v.Y, Z = v.Z;
+    double x2 = X * X, y2 = Y * Y, z2 = Z * Z;
+    d[0] = ((Y - 1) * (Z - 1) * (Y + 2*X + Z + 1)) / 8;
+    d[1] = -((Y + 1) * (Z - 1) * (2*X - Y + Z + 1)) / 8;
+    d[2] = -((Y + 1) * (Z - 1) * (Y + 2*X - Z - 1)) / 8;
+    d[3] = -((Y - 1) * (Z - 1) * (Y - 2*X + Z + 1)) / 8;
+    d[4] = -((Y - 1) * (Z + 1) * (Y + 2*X - Z + 1)) / 8;
+    d[5] = -((Y + 1) * (Z + 1) * (Y - 2*X + Z - 1)) / 8;
+    d[6] = ((Y + 1) * (Z + 1) * (Y + 2*X + Z - 1)) / 8;
+    d[7] = ((Y - 1) * (Z + 1) * (Y - 2*X - Z + 1)) / 8;
+    d[8] = -((y2 - 1) * (Z - 1)) / 4;
+    d[9] = (X * (Y + 1) * (Z - 1)) / 2;
+    d[10] = ((y2 - 1) * (Z - 1)) / 4;
+    d[11] = -(X * (Y - 1) * (Z - 1)) / 2;
+    d[12] = ((y2 - 1) * (Z + 1)) / 4;
+    d[13] = -(X * (Y + 1) * (Z + 1)) / 2;
+    d[14] = -((y2 - 1) * (Z + 1)) / 4;
+    d[15] = (X * (Y - 1) * (Z + 1)) / 2;
+    d[16] = -((z2 - 1) * (Y - 1)) / 4;
+    d[17] = ((z2 - 1) * (Y + 1)) / 4;
+    d[18] = -((z2 - 1) * (Y + 1)) / 4;
+    d[19] = ((z2 - 1) * (Y - 1)) / 4;
+    d[20] = ((X - 1) * (Z - 1) * (2*Y + X + Z + 1)) / 8;
+    d[21] = -((X - 1) * (Z - 1) * (X - 2*Y + Z + 1)) / 8;
+    d[22] = -((X + 1) * (Z - 1) * (2*Y + X - Z - 1)) / 8;
+    d[23] = -((X + 1) * (Z - 1) * (2*Y - X + Z + 1)) / 8;
+    d[24] = -((X - 1) * (Z + 1) * (2*Y + X - Z + 1)) / 8;
+    d[25] = -((X - 1) * (Z + 1) * (2*Y - X + Z - 1)) / 8;
+    d[26] = ((X + 1) * (Z + 1) * (2*Y + X + Z - 1)) / 8;
+    d[27] = ((X + 1) * (Z + 1) * (2*Y - X - Z + 1)) / 8;
+    d[28] = -(Y * (X - 1) * (Z - 1)) / 2;
+    d[29] = ((x2 - 1) * (Z - 1)) / 4;
+    d[30] = (Y * (X + 1) * (Z - 1)) / 2;
+    d[31] = -((x2 - 1) * (Z - 1)) / 4;
+    d[32] = (Y * (X - 1) * (Z + 1)) / 2;
+    d[33] = -((x2 - 1) * (Z + 1)) / 4;
+    d[34] = -(Y * (X + 1) * (Z + 1)) / 2;
+    d[35] = ((x2 - 1) * (Z + 1)) / 4;
+    d[36] = -((z2 - 1) * (X - 1)) / 4;
+    d[37] = ((z2 - 1) * (X - 1)) / 4;
+    d[38] = -((z2 - 1) * (X + 1)) / 4;
+    d[39] = ((z2 - 1) * (X + 1)) / 4;
+    d[40] = ((Y - 1) * (X - 1) * (Y + X + 2*Z + 1)) / 8;
+    d[41] = -((Y + 1) * (X - 1) * (X - Y + 2*Z + 1)) / 8;
+    d[42] = -((Y + 1) * (X + 1) * (Y + X - 2*Z - 1)) / 8;
+    d[43] = -((Y - 1) * (X + 1) * (Y - X + 2*Z + 1)) / 8;
+    d[44] = -((Y - 1) * (X - 1) * (Y + X - 2*Z + 1)) / 8;
+    d[45] = -((Y + 1) * (X - 1) * (Y - X + 2*Z - 1)) / 8;
+    d[46] = ((Y + 1) * (X + 1) * (Y + X + 2*Z - 1)) / 8;
+    d[47] = ((Y - 1) * (X + 1) * (Y - X - 2*Z + 1)) / 8;
+    d[48] = -((y2 - 1) * (X - 1)) / 4;
+    d[49] = ((x2 - 1) * (Y + 1)) / 4;
+    d[50] = ((y2 - 1) * (X + 1)) / 4;
+    d[51] = -((x2 - 1) * (Y - 1)) / 4;
+    d[52] = ((y2 - 1) * (X - 1)) / 4;
+    d[53] = -((x2 - 1) * (Y + 1)) / 4;
+    d[54] = -((y2 - 1) * (X + 1)) / 4;
+    d[55] = ((x2 - 1) * (Y - 1)) / 4;
+    d[56] = -(Z * (Y - 1) * (X - 1)) / 2;
+    d[57] = (Z * (Y + 1) * (X - 1)) / 2;
+    d[58] = -(Z * (Y + 1) * (X + 1)) / 2;
+    d[59] = (Z * (Y - 1) * (X + 1)) / 2;
     return d;
   }
   void Quadrature(std::vector<r3::Vec> &p, std::vector<double> &w) const override { // hexa20.go:166-176
@@ -345,27 +463,38 @@ struct Quad8 : IsoBase {
   int LenNodes() const override { return 8; }
   fem::DofsFlag Dofs() const override { return NodeDofs ? NodeDofs : fem::DofsFlag(fem::DofPosX | fem::DofPosY); }
   std::vector<r3::Vec> IsoparametricNodes() const override { std::vector<r3::Vec> n; for (auto &p : P) n.push_back({p[0], p[1], 0}); return n; }
-  static void eval(int a, double x, double y, double &N, double &gx, double &gy) {
-    const double px = P[a][0], py = P[a][1];
-    if (px != 0 && py != 0) { // corner: (1+xx_a)(1+yy_a)(xx_a+yy_a-1)/4
-      const double fx = 1 + x * px, fy = 1 + y * py, s = x * px + y * py - 1;
-      N = fx * fy * s / 4; gx = px * fy * (s + fx) / 4; gy = py * fx * (s + fy) / 4;
-    } else if (px == 0) {     // (1-x^2)(1+yy_a)/2
-      const double fy = 1 + y * py;
-      N = (1 - x * x) * fy / 2; gx = -x * fy; gy = (1 - x * x) * py / 2;
-    } else {                  // (1+xx_a)(1-y^2)/2
-      const double fx = 1 + x * px;
-      N = fx * (1 - y * y) / 2; gx = px * (1 - y * y) / 2; gy = -y * fx;
-    }
-  }
-  std::vector<double> Basis(r3::Vec v) const override {
-    std::vector<double> N(8); double gx, gy;
-    for (int a = 0; a < 8; ++a) eval(a, v.X, v.Y, N[a], gx, gy);
+  std::vector<double> Basis(r3::Vec v) const override { // quad8.go:51-63: the reference's expansion, term by term (same rounding)
+    std::vector<double> N(8);
+    const double x = v.X, y = v.Y;
+    N[0] = 0.25 * (1 - x) * (1 - y) * (-1 - x - y);
+    N[1] = 0.25 * (1 + x) * (1 - y) * (-1 + x - y);
+    N[2] = 0.25 * (1 + x) * (1 + y) * (-1 + x + y);
+    N[3] = 0.25 * (1 - x) * (1 + y) * (-1 - x + y);
+    N[4] = 0.5 * (1 - x) * (1 + x) * (1 - y);
+    N[5] = 0.5 * (1 + x) * (1 + y) * (1 - y);
+    N[6] = 0.5 * (1 - x) * (1 + x) * (1 + y);
+    N[7] = 0.5 * (1 - x) * (1 - y) * (1 + y);
     return N;
   }
-  std::vector<double> BasisDiff(r3::Vec v) const override {
-    std::vector<double> d(16); double N;
-    for (int a = 0; a < 8; ++a) eval(a, v.X, v.Y, N, d[a], d[8 + a]);
+  std::vector<double> BasisDiff(r3::Vec v) const override { // quad8.go:66-88: the reference's expansion, term by term (same rounding)
+    std::vector<double> d(16);
+    const double x = v.X, y = v.Y;
+    d[0] = -(x/4-1./4)*(y-1) - ((y-1)*(x+y+1))/4;
+    d[1] = ((y-1)*(y-x+1))/4 - (x/4+1./4)*(y-1);
+    d[2] = (x/4+1./4)*(y+1) + ((y+1)*(x+y-1))/4;
+    d[3] = (x/4-1./4)*(y+1) + ((y+1)*(x-y+1))/4;
+    d[4] = ((x+1)*(y-1))/2 + (x/2-1./2)*(y-1);
+    d[5] = -((y - 1) * (y + 1)) / 2;
+    d[6] = -((x+1)*(y+1))/2 - (x/2-1./2)*(y+1);
+    d[7] = ((y - 1) * (y + 1)) / 2;
+    d[8] = -(x/4-1./4)*(y-1) - (x/4-1./4)*(x+y+1);
+    d[9] = (x/4+1./4)*(y-x+1) + (x/4+1./4)*(y-1);
+    d[10] = (x/4+1./4)*(y+1) + (x/4+1./4)*(x+y-1);
+    d[11] = (x/4-1./4)*(x-y+1) - (x/4-1./4)*(y+1);
+    d[12] = (x/2 - 1./2) * (x + 1);
+    d[13] = -(x/2+1./2)*(y-1) - (x/2+1./2)*(y+1);
+    d[14] = -(x/2 - 1./2) * (x + 1);
+    d[15] = (x/2-1./2)*(y-1) + (x/2-1./2)*(y+1);
     return d;
   }
   int order() const { return QuadratureOrder <= 0 ? 3 : QuadratureOrder; } // quad8.go:98-104
