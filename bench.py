@@ -12,8 +12,9 @@ solids.Isotropic{E:200e9, Poisson:0.3}.Solid3D().
           on the library's stream, L2 flushed between steps.
   e2e   : the same through the reference-facing host API with HOST buffers (pinned): H2D of nodes and int64
           connectivity, assembly, D2H of the full CSR K into pinned host arrays, all inside the timed region.
-  roofline     : dominant kernel (k_noderows: B^T C B products fused with the deterministic row reduction) against the
-                 measured HBM copy bandwidth of MEASURED_PEAKS.json; FP64 / copy peaks probed in the same process.
+  roofline     : dominant kernel (config 1: k_srows_fused -- B^T C B per scalar CSR row fused with the deterministic row
+                 reduction) against the SURVEY 8(d) roofs: dense-contract flops over the FP64 peak probed in this run, and
+                 algorithmic bytes over the measured HBM copy bandwidth of MEASURED_PEAKS.json; the slower roof is `bound`.
   reassemble_cached_pattern : numeric-only re-assembly on the cached symbolic plan (femb200_reassemble).
   cpu_baseline : the CPU oracle (C port of the reference algorithm, single thread like the reference) timed on
                  this box's host cores on the same workload.
@@ -599,7 +600,9 @@ def main():
     # on the library's stream right before and after the launch), averaged over the timed steps.
     peak, peak_src = measured_peaks()
     names = list(pkg.TIMER_NAMES)
-    kern_ms = float(ph_mean[names.index("k_rows")])
+    # (elements with more than 4 nodes: the numeric phase is several kernels of comparable weight -- geometry, element
+    # blocks, ordered row gather -- and is taken as a whole)
+    kern_ms = float(ph_mean[names.index("k_rows" if nn <= 4 else "numeric_rows")])
     probe = (C.c_double * 2)()
     rc = L.femb200_probe_peaks(ctx_holder.ctx, 5, probe)
     p64 = float(probe[0]) if rc == 0 and probe[0] > 0 else 37.2     # TFLOP/s: measured DFMA probe, else 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
@@ -621,7 +624,8 @@ def main():
     step_roof_ms = max(f_tot / (p64 * 1e12) * 1e3, cbytes / (peak * 1e9) * 1e3)
     roofline = {"bound": "fp64" if fp64_bound else "hbm",
                 "kernel": "k_srows_fused (per-element B^T C B per scalar CSR row, geometry recomputed from row-cached coordinates, fused with the "
-                          "deterministic segmented reduction)" if nn <= 4 else "k_noderows (B^T C B per node row fused with the deterministic segmented reduction)",
+                          "deterministic segmented reduction)" if nn <= 4 else "numeric phase: k_geometry + k_elem_blocks (3x3 blocks of every element matrix through the gradient moment) + "
+                          "k_rows_gather (ordered per-row sum); k_geometry + k_noderows for the element kinds outside the element-block path",
                 "achieved": k_tf if fp64_bound else k_hbm, "peak": p64 if fp64_bound else peak, "unit": "TFLOP/s" if fp64_bound else "GB/s",
                 "frac": (t_fp64_ms if fp64_bound else t_hbm_ms) / kern_ms, "traffic": None,
                 "peak_source": ("FP64 vector peak measured in this run by femb200_probe_peaks (MEASURED_PEAKS.json holds no FP64 figure)" if fp64_bound else peak_src),
