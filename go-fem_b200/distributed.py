@@ -1,5 +1,8 @@
-"""Multi-GPU assembly: element partition in space-filling-curve order, one process per GPU, row-block
-ownership, and the exchange of interface rows (BASELINE.json north_star).
+"""Round-1 row-exchange variant of the multi-GPU assembly (kept for its gloo tests; the product path is the owner-computes
+scheme behind the C ABI, csrc/dist.cu: femb200_dist_* / femb200_group_*, DESIGN.md section 7, which needs no collective).
+
+Element partition in space-filling-curve order, one process per GPU, row-block ownership, and the exchange of interface
+rows (the NCCL reduce-scatter style scheme BASELINE.json's north_star names; measured at 60-68 % weak-scaling efficiency):
 
     rank p:  K_p  = assemble(elements of chunk p)                   local symbolic + numeric on its GPU
              for q != p: send the rows of K_p owned by q            pack (device gathers) -> all-to-all (NCCL / NVLink)
@@ -336,47 +339,6 @@ def exchange_and_own(backend, plan, device, dist, timings=None):
     return sum(int(p[3].numel()) * 12 + int(p[0].numel()) * 16 for p in pieces)   # bytes sent (values+indices, rows+lens)
 
 
-def exchange_into_owned(owned, outgoing, plan, device, dist, timings=None):
-    """Optimised collective step (what bench.py times).  `owned` was assembled with the node mask of the rank's
-    row block over [own elements ; halo elements (pattern only)], so it IS the row block with its final pattern
-    and the rank's own contributions; `outgoing` was assembled with the mask of the foreign nodes over the own
-    elements that touch them, so it holds exactly the interface rows to send.  Nothing is computed and then
-    dropped, and the received values are added in place in ascending source-rank order."""
-    import time
-    import torch
-
-    def mark(name, t0):
-        if timings is not None:
-            if device.type == "cuda":
-                torch.cuda.synchronize()
-            timings[name] = timings.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
-        return time.perf_counter()
-
-    t0 = time.perf_counter()
-    indptr, indices, values = outgoing.csr_tensors()
-    pieces = []
-    for q in range(plan.world):
-        rows = torch.as_tensor(plan.send_rows[q], device=device)
-        lens, idx, val = gather_rows(indptr, indices, values, rows)
-        pieces.append((rows, lens, idx, val))
-    t0 = mark("pack", t0)
-    received = all_to_all_ragged(pieces, plan.world, plan.rank, device, dist)
-    t0 = mark("all_to_all", t0)
-    for q in range(plan.world):                      # fixed order: ascending source rank
-        if q == plan.rank:
-            continue
-        rows, lens, idx, val = received[q]
-        if rows.numel() == 0:
-            continue
-        ptr0 = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=device)
-        torch.cumsum(lens, 0, out=ptr0[1:])
-        if not owned.add_entries(rows, ptr0, idx, val):
-            owned.accumulate_rows(rows, ptr0, idx, val)
-    mark("accumulate", t0)
-    return sum(int(p[3].numel()) * 12 + int(p[0].numel()) * 16 for p in pieces)
-
-
-# ----------------------------------------------------------------------------- backends
 class DeviceView:
     """Zero-copy torch view of library-owned device memory (via __cuda_array_interface__)."""
 
