@@ -53,6 +53,7 @@ def lib():
     L.femb200_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.femb200_ctx_destroy.argtypes = [vp]
     L.femb200_ctx_set_stream.argtypes = [vp, vp]
+    L.femb200_ctx_trim.argtypes = [vp]
     L.femb200_ctx_set_concurrent.argtypes = [vp, C.c_int32]
     L.femb200_last_cuda_error.argtypes = [vp]
     L.femb200_last_cuda_error.restype = C.c_char_p

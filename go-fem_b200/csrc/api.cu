@@ -82,6 +82,18 @@ void femb200_ctx_destroy(femb200_ctx *ctx) {
   delete ctx;
 }
 
+int femb200_ctx_trim(femb200_ctx *ctx) {
+  if (!ctx) return FEMB200_ERR_BAD_ARG;
+  FEMB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  scratch_release(ctx, true);
+  ctx->scratch_hint = 0;
+  if (ctx->cub_tmp) { cudaFreeAsync(ctx->cub_tmp, ctx->stream); ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0; }
+  FEMB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->pool) FEMB_CUDA_OK(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
+  return 0;
+}
+
 int femb200_ctx_set_stream(femb200_ctx *ctx, void *s) {
   if (!ctx) return FEMB200_ERR_BAD_ARG;
   cudaStreamSynchronize(ctx->stream);

@@ -80,6 +80,23 @@ func releaseCtx(device int) {
 	}
 }
 
+// TrimDevice returns the scratch arena of `device`'s shared context to the GPU (femb200_ctx_trim): worth calling after a
+// large one-off assembly when a solver is about to use the same device.  No-op if no assembler lives on the device.
+func TrimDevice(device int) error {
+	ctxMu.Lock()
+	d, ok := ctxs[device]
+	ctxMu.Unlock()
+	if !ok {
+		return nil
+	}
+	d.mu.Lock()
+	defer d.mu.Unlock()
+	if rc := C.femb200_ctx_trim(d.ctx); rc != 0 {
+		return fmt.Errorf("femb200_ctx_trim: error %d: %s", int(rc), C.GoString(C.femb200_last_cuda_error(d.ctx)))
+	}
+	return nil
+}
+
 // Assembler wraps one femb200_assembler (twin of fem.GeneralAssembler) on a shared device context.
 type Assembler struct {
 	dev    *deviceCtx

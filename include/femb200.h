@@ -85,6 +85,10 @@ int femb200_ctx_set_stream(femb200_ctx *ctx, void *cuda_stream);
  * instead of the device-wide __constant__ bank.  (A rank of the multi-GPU path assembles its owned row block and
  * its outgoing interface rows this way, the small second call filling the gaps of the first.) */
 int femb200_ctx_set_concurrent(femb200_ctx *ctx, int32_t on);
+/* Returns the context's per-call scratch arena to the device (it is kept between calls so that a repeated assembly
+ * allocates nothing; after a large one-off assembly -- the element-matrix staging of a Hexa20 mesh is 28.8 KB per
+ * element -- a caller that goes on to solve on the same GPU wants the memory back).  K and the cached plans are untouched. */
+int femb200_ctx_trim(femb200_ctx *ctx);
 const char *femb200_last_cuda_error(const femb200_ctx *ctx);
 
 /* fem.NewGeneralAssembler(nodes []r3.Vec, modelDofs) (assembler.go:21-28).

@@ -895,3 +895,34 @@ def test_collapsed_larger_elements(pkg, O, meshes, name):
     og.add_isoparametric(KINDS[name]["kind"], Cm, bk, conn)
     rp, ri, rv, ab = og.csr(with_absum=True)
     compare_csr(ga.Ksolid().csr(), (rp, ri, rv), ab, TOL)
+
+
+def test_ctx_trim_releases_the_scratch_arena(pkg, meshes):
+    """femb200_ctx_trim hands the per-call scratch arena (here: the element-matrix staging of a Hexa20 mesh) back to the device;
+    K stays valid and the next assembly on the same context reproduces it bit for bit."""
+    import torch
+    nodes, conn = meshes.mesh_for("hexa20", 12)
+    ra = pkg.RawAssembler(nodes, 3)
+    desc = ra.make_desc(pkg.elements.Hexa20(), pkg.solids.Isotropic(200e9, 0.3).Solid3D())
+    assert ra.add(desc, conn=conn) == 0
+    k1 = [a.copy() for a in ra.csr()]
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    assert pkg.lib().femb200_ctx_trim(ra.ctx) == 0
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free1 - free0 >= conn.shape[0] * 3600 * 8          # at least the staging array came back
+    k1b = ra.csr()
+    assert all(np.array_equal(a, b) for a, b in zip(k1, k1b))
+    import ctypes as C
+    L = pkg.lib()
+    h = C.c_void_p()                                           # a second assembler on the SAME (trimmed) context
+    nodes_c = np.ascontiguousarray(nodes, dtype=np.float64)
+    assert L.femb200_assembler_create(ra.ctx, C.c_void_p(nodes_c.ctypes.data), nodes_c.shape[0], 3, 0, C.byref(h)) == 0
+    conn32 = np.ascontiguousarray(conn, dtype=np.int32)
+    assert L.femb200_add_isoparametric(h, C.byref(desc), C.c_void_p(conn32.ctypes.data), 0, 0, conn32.shape[0]) == 0
+    nnz = L.femb200_nnz(h)
+    ip, ix, v = np.empty(3 * nodes.shape[0] + 1, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+    assert L.femb200_csr_copy(h, C.c_void_p(ip.ctypes.data), C.c_void_p(ix.ctypes.data), C.c_void_p(v.ctypes.data)) == 0
+    assert np.array_equal(ip, k1[0]) and np.array_equal(ix, k1[1]) and np.array_equal(v, k1[2])
+    L.femb200_assembler_destroy(h)
+    ra.close()
