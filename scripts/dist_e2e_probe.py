@@ -40,6 +40,7 @@ for it in range(reps + 2):
     h = C.c_void_p()
     assert L.femb200_dist_create(ctx, rank, world, h_nodes.data_ptr(), 0, n_nodes, 3, h_conn.data_ptr(), 0, 0, n_elem, 4, 1, C.byref(h)) == 0
     torch.cuda.synchronize(); t.append(time.perf_counter())
+    _o = (C.c_int64 * 8)(); _pm = C.c_float(); L.femb200_dist_info(h, _o, C.byref(_pm)); part_ms = _pm.value
     assert L.femb200_dist_add_isoparametric(h, C.byref(desc)) == 0
     torch.cuda.synchronize(); t.append(time.perf_counter())
     assert L.femb200_csr_copy(L.femb200_dist_assembler(h), h_indptr.data_ptr(), h_indices.data_ptr(), h_values.data_ptr()) == 0
@@ -48,5 +49,7 @@ for it in range(reps + 2):
     torch.cuda.synchronize(); t.append(time.perf_counter())
     if it >= 2:
         acc += np.diff(t)
+    if os.environ.get('PROBE_VERBOSE'):
+        print('   iter', it, ' '.join(f'{1e3*x:.2f}' for x in np.diff(t)), f'partition(device events) {part_ms:.2f}', flush=True)
 acc *= 1e3 / reps
 print(f"world={world} rank={rank} N={N} elements={n_elem} local={info['local_elems']} nnz_rank={nnz}: create {acc[0]:.2f} ms (H2D {(h_nodes.numel()*8+h_conn.numel()*4)/1e6:.0f} MB, partition on device {info['partition_ms']:.2f} ms)  add {acc[1]:.2f}  csr_copy {acc[2]:.2f} ({(h_indptr.numel()*8+h_indices.numel()*4+h_values.numel()*8)/1e6:.0f} MB)  destroy {acc[3]:.2f}  total {acc.sum():.2f} ms")
