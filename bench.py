@@ -279,6 +279,11 @@ def run_multi_gpu(args, rank, world, local_rank):
     holder = pkg.RawAssembler(np.zeros((1, 3)), 3, device=local_rank)
     ctx = holder.ctx
     dn, n_nodes, dc, n_elem = pkg.device_mesh_bcc_tetra4(ctx, N, N, N, 1.0 / N)
+    # the first partition of a process grows the context's scratch arena (a one-off cost); the figure reported is the second one
+    d = pkg.DistRank(ctx, rank, world, 3, 4, nodes_ptr=dn, conn_ptr=dc, n_nodes=n_nodes, n_elem=n_elem, order_mode=1)
+    part_first_ms = d.info()["partition_ms"]
+    d.close()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     d = pkg.DistRank(ctx, rank, world, 3, 4, nodes_ptr=dn, conn_ptr=dc, n_nodes=n_nodes, n_elem=n_elem, order_mode=1)
     part_wall = time.perf_counter() - t0
@@ -397,7 +402,8 @@ def run_multi_gpu(args, rank, world, local_rank):
                                         "NCCL reduce-scatter variant measured 60-68 % efficiency in round 1, see DESIGN.md section 7)"},
                 "dofs_per_s": value * 3 * n_nodes / n_elem, "nnz_total": tot[0].item(),
                 "redundant_halo_elements_total": tot[1].item(), "local_elements_max": mx[2].item(),
-                "partition": {"ms_device_max": mx[3].item(), "s_wall_rank0": part_wall, "where": "on the device, every rank over the whole mesh (no communication)"},
+                "partition": {"ms_device_max": mx[3].item(), "ms_device_first_call_rank0": part_first_ms, "s_wall_rank0": part_wall,
+                              "where": "on the device, every rank over the whole mesh (no communication)"},
                 "phases_ms_rank0": dict(zip(names, [float(x) for x in ph_mean])),
                 "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": bytes_io[0].item(), "d2h_bytes_per_step": bytes_io[1].item(),
                         "ms_per_step": 1e3 * float(te.item()),
