@@ -338,38 +338,57 @@ def run_multi_gpu(args, rank, world, local_rank):
     h_indptr = torch.empty(n_local_dofs + 1, dtype=torch.int64).pin_memory()
     h_indices = torch.empty(nnz_rank, dtype=torch.int32).pin_memory()
     h_values = torch.empty(nnz_rank, dtype=torch.float64).pin_memory()
+    h_blkptr = torch.empty(info["local_nodes"] + 1, dtype=torch.int64).pin_memory()
+    h_blkcols = torch.empty(nnz_rank // 9, dtype=torch.int32).pin_memory()
+    h_l2g = torch.empty(info["local_nodes"], dtype=torch.int32).pin_memory()
+    h_owned = torch.empty(info["local_nodes"], dtype=torch.uint8).pin_memory()
 
-    def e2e_step():
+    def e2e_step(block):
+        # block=True (as at N=1): the row block leaves as node-block pattern + values (femb200_bsr_copy; block columns are LOCAL
+        # node ids) plus the local->global node map and the owned-row mask (femb200_dist_local_nodes); block=False: the scalar
+        # CSR with global column ids (femb200_csr_copy)
         h = C.c_void_p()
         rc = L.femb200_dist_create(ctx, rank, world, h_nodes.data_ptr(), 0, n_nodes, 3, h_conn.data_ptr(), 0, 0, n_elem, 4, 1, C.byref(h))
         assert rc == 0, rc
         rc = L.femb200_dist_add_isoparametric(h, C.byref(desc))
         assert rc == 0, rc
-        rc = L.femb200_csr_copy(L.femb200_dist_assembler(h), h_indptr.data_ptr(), h_indices.data_ptr(), h_values.data_ptr())
+        if block:
+            rc = L.femb200_bsr_copy(L.femb200_dist_assembler(h), h_blkptr.data_ptr(), h_blkcols.data_ptr(), h_values.data_ptr())
+            assert rc == 0, rc
+            rc = L.femb200_dist_local_nodes(h, h_l2g.data_ptr(), h_owned.data_ptr())
+        else:
+            rc = L.femb200_csr_copy(L.femb200_dist_assembler(h), h_indptr.data_ptr(), h_indices.data_ptr(), h_values.data_ptr())
         assert rc == 0, rc
         L.femb200_dist_destroy(h)
 
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    e2e_t = []
-    for _ in range(e2e_steps):
+
+    def time_e2e(block):
+        for _ in range(2):
+            e2e_step(block)
         torch.cuda.synchronize()
         dist.barrier()
-        t0 = time.perf_counter()
-        e2e_step()
-        e2e_t.append(time.perf_counter() - t0)
-    te = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device=dev)
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    bytes_io = torch.tensor([float(h_nodes.numel() * 8 + h_conn.numel() * 4), float(h_indptr.numel() * 8 + h_indices.numel() * 4 + h_values.numel() * 8)],
-                            dtype=torch.float64, device=dev)
+        ts = []
+        for _ in range(e2e_steps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            e2e_step(block)
+            ts.append(time.perf_counter() - t0)
+        tt = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt
+
+    te = time_e2e(True)
+    te_scalar = time_e2e(False)
+    bytes_io = torch.tensor([float(h_nodes.numel() * 8 + h_conn.numel() * 4),
+                             float(h_blkptr.numel() * 8 + h_blkcols.numel() * 4 + h_values.numel() * 8 + h_l2g.numel() * 4 + h_owned.numel()),
+                             float(h_indptr.numel() * 8 + h_indices.numel() * 4 + h_values.numel() * 8)], dtype=torch.float64, device=dev)
     dist.all_reduce(bytes_io)
     d.close()
     L.femb200_mesh_free(ctx, dn)
     L.femb200_mesh_free(ctx, dc)
-    del flush, h_nodes, h_conn, h_indptr, h_indices, h_values
+    del flush, h_nodes, h_conn, h_indptr, h_indices, h_values, h_blkptr, h_blkcols, h_l2g, h_owned
     torch.cuda.empty_cache()
 
     # ---- strong scaling on the 101 M-element mesh -----------------------------------------------------------------------------
@@ -407,8 +426,12 @@ def run_multi_gpu(args, rank, world, local_rank):
                 "phases_ms_rank0": dict(zip(names, [float(x) for x in ph_mean])),
                 "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": bytes_io[0].item(), "d2h_bytes_per_step": bytes_io[1].item(),
                         "ms_per_step": 1e3 * float(te.item()),
-                        "note": "per rank: whole mesh in from pinned host memory (nodes f64 + int32 connectivity), partition + assembly, the rank's CSR row block "
-                                "(indptr int64, global indices int32, values f64) out to pinned host memory; host clock, max over ranks; bytes summed over ranks"},
+                        "note": "per rank: whole mesh in from pinned host memory (nodes f64 + int32 connectivity), partition + assembly, the rank's row block out "
+                                "to pinned host memory as node-block pattern + values (femb200_bsr_copy: blkptr int64, blkcols int32 local node ids, values f64) "
+                                "with the local->global node map and the owned-row mask (femb200_dist_local_nodes); host clock, max over ranks; bytes summed over ranks",
+                        "scalar_csr_variant": {"value": n_elem / float(te_scalar.item()), "ms_per_step": 1e3 * float(te_scalar.item()),
+                                               "d2h_bytes_per_step": bytes_io[2].item(),
+                                               "note": "femb200_csr_copy: indptr int64 + GLOBAL scalar indices int32 + values f64"}},
                 "strong_scaling_S": s_line,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None}
         emit(line)

@@ -540,7 +540,7 @@ int femb200_csr_copy(const femb200_assembler *ga, int64_t *indptr, int32_t *indi
 }
 
 int64_t femb200_bsr_blocks(const femb200_assembler *ga) {
-  if (!ga || !ga->plan.matches_K || !ga->plan.identity || !ga->plan.blkcols || ga->d_col_map) return -1;
+  if (!ga || !ga->plan.matches_K || !ga->plan.identity || !ga->plan.blkcols) return -1;
   return ga->plan.nblk;
 }
 

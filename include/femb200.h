@@ -140,7 +140,8 @@ int femb200_csr_copy(const femb200_assembler *ga, int64_t *indptr, int32_t *indi
  * blkptr[n_nodes+1] int64, blkcols[nblk] int32 = column NODE of every block (ascending within a row),
  * values[nnz] exactly as in femb200_csr_copy.  Scalar row (I, i) of K has the columns mdpn*blkcols[p] + j,
  * p in [blkptr[I], blkptr[I+1]), j in [0, mdpn), and starts at values[mdpn*mdpn*blkptr[I] + i*mdpn*(blkptr[I+1]-blkptr[I])].
- * NULL pointers are skipped; femb200_bsr_blocks returns nblk. */
+ * NULL pointers are skipped; femb200_bsr_blocks returns nblk.  On an assembler with a column map (the rank-local assembler of
+ * femb200_dist_*) blkcols are rank-LOCAL node ids: global column node = l2g[blkcols[p]] with l2g from femb200_dist_local_nodes. */
 int64_t femb200_bsr_blocks(const femb200_assembler *ga);
 int femb200_bsr_copy(const femb200_assembler *ga, int64_t *blkptr, int32_t *blkcols, double *values);
 /* The same arrays left on the device (valid until the next add/destroy). */

@@ -134,3 +134,33 @@ def test_device_mesh_generator_equals_the_numpy_one(pkg, meshes, dims):
     pkg.lib().femb200_mesh_free(holder.ctx, dn)
     pkg.lib().femb200_mesh_free(holder.ctx, dc)
     holder.close()
+
+
+def test_rank_row_block_as_block_pattern(pkg, meshes):
+    """femb200_bsr_copy on a rank's assembler: block columns are rank-LOCAL node ids; with the local->global map of
+    femb200_dist_local_nodes they reproduce the GLOBAL scalar indices of femb200_csr_copy, values identical."""
+    import ctypes as C
+    nodes, conn = meshes.mesh_for("tetra4", 6)
+    holder = pkg.RawAssembler(nodes, 3)
+    desc = holder.make_desc(pkg.elements.Tetra4(), pkg.solids.Isotropic(200e9, 0.3).Solid3D())
+    L = pkg.lib()
+    for r in range(2):
+        d = pkg.DistRank(holder.ctx, r, 2, 3, 4, nodes=nodes, conn=conn, order_mode=1)
+        assert d.add(desc) == 0
+        ga = d.assembler()
+        n_local = d.info()["local_nodes"]
+        nnz = L.femb200_nnz(ga)
+        nblk = L.femb200_bsr_blocks(ga)
+        assert nblk * 9 == nnz
+        indptr, indices, values = np.zeros(3 * n_local + 1, np.int64), np.zeros(nnz, np.int32), np.zeros(nnz)
+        assert L.femb200_csr_copy(ga, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data) == 0
+        blkptr, blkcols, bvals = np.zeros(n_local + 1, np.int64), np.zeros(nblk, np.int32), np.zeros(nnz)
+        assert L.femb200_bsr_copy(ga, blkptr.ctypes.data, blkcols.ctypes.data, bvals.ctypes.data) == 0
+        l2g, owned = d.local_nodes()
+        assert np.array_equal(bvals, values)
+        assert np.array_equal(indptr[::3], 9 * blkptr) and np.all((np.diff(blkptr) > 0) <= (owned != 0))
+        gcols = (l2g[blkcols].astype(np.int64)[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+        idx = np.concatenate([np.tile(gcols[3 * blkptr[I]:3 * blkptr[I + 1]], 3) for I in range(n_local)])
+        assert np.array_equal(idx.astype(np.int32), indices)
+        d.close()
+    holder.close()
