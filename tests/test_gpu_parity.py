@@ -926,3 +926,31 @@ def test_ctx_trim_releases_the_scratch_arena(pkg, meshes):
     assert np.array_equal(ip, k1[0]) and np.array_equal(ix, k1[1]) and np.array_equal(v, k1[2])
     L.femb200_assembler_destroy(h)
     ra.close()
+
+
+@pytest.mark.parametrize("name,size,mode,flags", [("tetra4", 5, 0, 7), ("hexa8", 4, 0, 7), ("tetra10", 2, 0, 7), ("hexa20", 2, 0, 7),
+                                                  ("quad4", 9, 1, 3), ("quad8", 5, 3, 3)])
+def test_pattern_only_elements(pkg, O, meshes, name, size, mode, flags):
+    """femb200_add_isoparametric_halo: the trailing n_pattern_only elements contribute their sparsity pattern and no values (a
+    rank of the row-exchange variant lists its halo that way).  Every numeric path stops a row's sum at its first
+    pattern-only element: the fused kernel (Tetra4, Quad4), the element-block gather (Hexa8, Tetra10, Hexa20) and the
+    node-row kernel (Quad8).  Expectation: the oracle with the halo assembled from a zero material."""
+    nodes, conn = meshes.mesh_for(name, size)
+    n_own = (2 * conn.shape[0]) // 3
+    own, halo = conn[:n_own], conn[n_own:]
+    mdpn = bin(flags).count("1")
+    ra = pkg.RawAssembler(nodes, mdpn)
+    desc = ra.make_desc(elem_of(pkg, name), constituter_of(pkg, mode, 200e9, 0.3))
+    assert ra.add(desc, conn=conn, n_pattern_only=halo.shape[0]) == 0
+    Cm, bk = O.constitutive(mode, 200e9, 0.3)
+    og = O.GeneralAssembler(nodes, flags)
+    og.add_isoparametric(KINDS[name]["kind"], Cm, bk, own)
+    og.add_isoparametric(KINDS[name]["kind"], Cm * 0.0, bk, halo)
+    rp, ri, rv, ab = og.csr(with_absum=True)
+    # the zero-material pass adds nothing to the normaliser of the halo-only entries: give those an absolute scale
+    got = ra.csr()
+    assert np.array_equal(got[0], rp) and np.array_equal(got[1], ri)
+    scale = np.maximum(np.abs(rv), ab)
+    assert np.all(np.abs(got[2] - rv) <= TOL * np.where(scale > 0, scale, 1.0))
+    assert np.all(got[2][scale == 0] == 0.0)
+    ra.close()
